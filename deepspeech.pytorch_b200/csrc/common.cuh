@@ -1,0 +1,103 @@
+// Shared host/device helpers for libds2_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+
+#include "../../include/ds2_b200.h"
+
+namespace ds2 {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+int precision();
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define DS2_CHECK_CUDA(expr)                                                             \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      ds2::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return DS2_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define DS2_REQUIRE(cond, ...)                      \
+  do {                                              \
+    if (!(cond)) {                                  \
+      ds2::set_error(__VA_ARGS__);                  \
+      return DS2_ERR_INVALID;                       \
+    }                                               \
+  } while (0)
+
+// Launch bookkeeping: every kernel launch of the library goes through this.
+#define DS2_LAUNCH(kernel, grid, block, smem, stream, ...)                \
+  do {                                                                    \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);           \
+    ds2::g_launches.fetch_add(1, std::memory_order_relaxed);              \
+    DS2_CHECK_CUDA(cudaGetLastError());                                   \
+  } while (0)
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+#ifdef __CUDACC__
+__device__ __forceinline__ int cdiv_dev(int a, int b) { return (a + b - 1) / b; }
+#endif
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over a caller-provided workspace.
+struct Arena {
+  char* base;
+  size_t cap, off;
+  Arena(void* p, size_t n) : base(static_cast<char*>(p)), cap(n), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t bytes = align_up(count * sizeof(T), 256);
+    if (off + bytes > cap) return nullptr;
+    T* r = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return r;
+  }
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif
+
+// ---- internal cross-file entry points -------------------------------------------------------
+// C[M,N] = alpha*op(A)op(B) + beta*C (row-major, fp32 FFMA kernel; any shape/stride)
+int gemm_simt(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+              int ldb, float beta, float* C, int ldc, cudaStream_t st);
+// tcgen05 TF32 kernel.  Returns 1 if the shape is not eligible (caller falls back to gemm_simt).
+int gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+            int ldb, float beta, float* C, int ldc, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t gemm_tc_workspace_bytes(int transA, int transB, int M, int N, int K);
+
+// BatchNorm over rows of a (rows, F) matrix (BatchNorm1d under SequenceWise, model.py:18-33,86,196)
+// training: batch stats (biased var) -> mean/invstd, running stats updated; else running stats.
+// y = (x-mean)*invstd*gamma+beta ; xhat optionally stored.
+int bn_rows_fwd(int rows, int F, const float* x, const float* gamma, const float* beta, float* rmean, float* rvar,
+                int training, float momentum, float eps, float* y, float* xhat, float* mean_invstd /*2F*/,
+                double* ws_sums /*2F doubles*/, cudaStream_t st);
+// y / xhat again from saved statistics (backward recomputation)
+int bn_rows_reapply(int rows, int F, const float* x, const float* gamma, const float* beta,
+                    const float* mean_invstd, float* y, float* xhat, cudaStream_t st);
+int transpose(int R, int C, const float* in, float* out, cudaStream_t st);
+// dx = gamma*invstd*(dy - mean(dy) - xhat*mean(dy*xhat)); dgamma, dbeta written.
+int bn_rows_bwd(int rows, int F, const float* xhat, const float* gamma, const float* mean_invstd, const float* dy,
+                float* dx, float* dgamma, float* dbeta, double* ws_sums /*2F doubles*/, cudaStream_t st);
+
+}  // namespace ds2

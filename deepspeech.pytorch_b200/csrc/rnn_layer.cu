@@ -1,0 +1,481 @@
+// One BatchRNN layer (model.py:80-102): [BatchNorm1d over T*B rows] -> input projection GEMM ->
+// recurrent sweep per direction with per-utterance length masking (replaces pack/pad)
+// -> sum of directions.  Backward: reverse sweep producing gate gradients in place of the saved
+// gate activations, then three dense GEMMs (dW_ih, dW_hh, dX) and the BatchNorm backward.
+//
+// This file holds the host orchestration and the generic FFMA step kernels (any H, any B): one
+// launch per time step covering both directions.  rnn_persistent_tc.cu provides the tcgen05
+// persistent sweep that replaces the step launches when the shape is eligible.
+//
+// reserve layout (floats):  gates (T,B,D,G*H) | hseq (D,T,B,H) | aux (D,T,B,H: LSTM cell states /
+//                           GRU W_hn h + b_hn; absent for tanh) | bn mean,invstd (2*In)
+#include "common.cuh"
+#include "rnn_cells.cuh"
+
+namespace ds2 {
+
+constexpr int UT = 8;   // hidden units per CTA
+constexpr int KC = 64;  // reduction chunk staged in shared memory
+
+struct SeqArgs {
+  int T, B, H, D, G;
+  const int32_t* len;
+  float* gates;  // (T,B,D,G*H)
+  float* hseq;   // (D,T,B,H)
+  float* aux;    // (D,T,B,H) or null
+  const float* w_hh[2];   // fwd: (G*H,H) ; bwd: transposed (H,G*H)
+  const float* b_ih[2];
+  const float* b_hh[2];
+  const float* h0;        // (D,B,H) or null
+  const float* c0;
+  const float* dy;        // bwd: (T,B,H)
+  float* carry;           // bwd: (D,B,H) dc (LSTM) / dh (GRU)
+  int training;
+};
+
+__device__ __forceinline__ int gates_per(int rnn) { return rnn == DS2_RNN_LSTM ? 4 : (rnn == DS2_RNN_GRU ? 3 : 1); }
+
+// grid (ceil(H/UT), D), block (32, UT)
+template <int RNN>
+__global__ void __launch_bounds__(32 * UT) rnn_step_fwd_kernel(SeqArgs a, int step) {
+  constexpr int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
+  __shared__ float hs[32][KC + 1];
+  __shared__ float ws[G * UT][KC + 1];
+  const int d = blockIdx.y, T = a.T, B = a.B, H = a.H, D = a.D;
+  const int t = d == 0 ? step : T - 1 - step;
+  const int tp = d == 0 ? t - 1 : t + 1;
+  const bool tp_in = tp >= 0 && tp < T;
+  const int lane = threadIdx.x, uy = threadIdx.y, tid = uy * 32 + lane;
+  const int u0 = blockIdx.x * UT, u = u0 + uy;
+  const float* __restrict__ W = a.w_hh[d];
+  const float* hprev = a.hseq + ((size_t)d * T + (tp_in ? tp : 0)) * B * H;
+  const float* cprev = a.aux ? a.aux + ((size_t)d * T + (tp_in ? tp : 0)) * B * H : nullptr;
+  const int GH = G * H;
+
+  for (int bt = 0; bt < (B + 31) / 32; ++bt) {
+    const int b = bt * 32 + lane;
+    float acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = 0.f;
+    for (int k0 = 0; k0 < H; k0 += KC) {
+      for (int idx = tid; idx < 32 * KC; idx += 32 * UT) {
+        int kk = idx % KC, bb = idx / KC, gb = bt * 32 + bb, gk = k0 + kk;
+        float v = 0.f;
+        if (gb < B && gk < H) {
+          bool pin = tp_in && (d == 0 || tp < a.len[gb]);
+          v = pin ? hprev[(size_t)gb * H + gk] : (a.h0 ? a.h0[((size_t)d * B + gb) * H + gk] : 0.f);
+        }
+        hs[bb][kk] = v;
+      }
+      for (int idx = tid; idx < G * UT * KC; idx += 32 * UT) {
+        int kk = idx % KC, rr = idx / KC, g = rr / UT, gu = u0 + rr % UT, gk = k0 + kk;
+        ws[rr][kk] = (gu < H && gk < H) ? W[((size_t)g * H + gu) * H + gk] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < KC; ++kk) {
+        float hv = hs[lane][kk];
+#pragma unroll
+        for (int g = 0; g < G; ++g) acc[g] = fmaf(hv, ws[g * UT + uy][kk], acc[g]);
+      }
+      __syncthreads();
+    }
+    if (b < B && u < H) {
+      const bool valid = t < a.len[b];
+      const bool pin = tp_in && (d == 0 || tp < a.len[b]);
+      float* gp = a.gates + (((size_t)t * B + b) * D + d) * GH + u;
+      float* hp = a.hseq + (((size_t)d * T + t) * B + b) * H + u;
+      float* xp = a.aux ? a.aux + (((size_t)d * T + t) * B + b) * H + u : nullptr;
+      const float* bi = a.b_ih[d] + u;
+      const float* bh = a.b_hh[d] + u;
+      if (!valid) {
+        *hp = 0.f;
+        if (xp) *xp = 0.f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) gp[g * H] = 0.f;
+      } else if constexpr (RNN == DS2_RNN_LSTM) {
+        float c_prev = pin ? cprev[(size_t)b * H + u] : (a.c0 ? a.c0[((size_t)d * B + b) * H + u] : 0.f);
+        LstmFwd r = lstm_cell_fwd(gp[0] + bi[0] + acc[0] + bh[0], gp[H] + bi[H] + acc[1] + bh[H],
+                                  gp[2 * H] + bi[2 * H] + acc[2] + bh[2 * H],
+                                  gp[3 * H] + bi[3 * H] + acc[3] + bh[3 * H], c_prev);
+        gp[0] = r.i; gp[H] = r.f; gp[2 * H] = r.g; gp[3 * H] = r.o;
+        *hp = r.h;
+        *xp = r.c;
+      } else if constexpr (RNN == DS2_RNN_GRU) {
+        float h_prev = pin ? hprev[(size_t)b * H + u] : (a.h0 ? a.h0[((size_t)d * B + b) * H + u] : 0.f);
+        float hn = acc[2] + bh[2 * H];
+        GruFwd r = gru_cell_fwd(gp[0] + bi[0], gp[H] + bi[H], gp[2 * H] + bi[2 * H], acc[0] + bh[0],
+                                acc[1] + bh[H], hn, h_prev);
+        gp[0] = r.r; gp[H] = r.z; gp[2 * H] = r.n;
+        *hp = r.h;
+        *xp = hn;
+      } else {
+        float h = tanhf(gp[0] + bi[0] + acc[0] + bh[0]);
+        gp[0] = h;
+        *hp = h;
+      }
+    }
+  }
+}
+
+// Backward step.  w_hh[d] here is the TRANSPOSED recurrent matrix (H, G*H).
+template <int RNN>
+__global__ void __launch_bounds__(32 * UT) rnn_step_bwd_kernel(SeqArgs a, int step) {
+  constexpr int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
+  __shared__ float gs[32][KC + 1];
+  __shared__ float ws[UT][KC + 1];
+  const int d = blockIdx.y, T = a.T, B = a.B, H = a.H, D = a.D;
+  const int t = d == 0 ? T - 1 - step : step;
+  const int tn = d == 0 ? t + 1 : t - 1;   // processed just before (later in this direction's time)
+  const int tp = d == 0 ? t - 1 : t + 1;   // source of the previous state in the forward sweep
+  const bool tn_in = tn >= 0 && tn < T, tp_in = tp >= 0 && tp < T;
+  const int lane = threadIdx.x, uy = threadIdx.y, tid = uy * 32 + lane;
+  const int u0 = blockIdx.x * UT, u = u0 + uy;
+  const int GH = G * H;
+  const float* __restrict__ WT = a.w_hh[d];
+
+  for (int bt = 0; bt < (B + 31) / 32; ++bt) {
+    const int b = bt * 32 + lane;
+    float acc = 0.f;
+    if (tn_in) {
+      for (int k0 = 0; k0 < GH; k0 += KC) {
+        for (int idx = tid; idx < 32 * KC; idx += 32 * UT) {
+          int kk = idx % KC, bb = idx / KC, gb = bt * 32 + bb, row = k0 + kk;
+          float v = 0.f;
+          if (gb < B && row < GH) {
+            if (RNN == DS2_RNN_GRU && row >= 2 * H)
+              v = a.aux[(((size_t)d * T + tn) * B + gb) * H + (row - 2 * H)];   // dGh_n
+            else
+              v = a.gates[(((size_t)tn * B + gb) * D + d) * GH + row];
+          }
+          gs[bb][kk] = v;
+        }
+        for (int idx = tid; idx < UT * KC; idx += 32 * UT) {
+          int kk = idx % KC, rr = idx / KC, gu = u0 + rr, row = k0 + kk;
+          ws[rr][kk] = (gu < H && row < GH) ? WT[(size_t)gu * GH + row] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < KC; ++kk) acc = fmaf(gs[lane][kk], ws[uy][kk], acc);
+        __syncthreads();
+      }
+    }
+    if (b < B && u < H) {
+      const bool valid = t < a.len[b];
+      const bool pin = tp_in && (d == 0 || tp < a.len[b]);
+      float* gp = a.gates + (((size_t)t * B + b) * D + d) * GH + u;
+      const size_t si = (((size_t)d * T + t) * B + b) * H + u;
+      const size_t sp = (((size_t)d * T + (tp_in ? tp : 0)) * B + b) * H + u;
+      float* carry = a.carry ? a.carry + ((size_t)d * B + b) * H + u : nullptr;
+      if (!valid) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) gp[g * H] = 0.f;
+        if (RNN == DS2_RNN_GRU) a.aux[si] = 0.f;
+      } else {
+        float dh = a.dy[((size_t)t * B + b) * H + u] + acc;
+        if constexpr (RNN == DS2_RNN_LSTM) {
+          float c_prev = pin ? a.aux[sp] : 0.f;
+          LstmBwd r = lstm_cell_bwd(gp[0], gp[H], gp[2 * H], gp[3 * H], a.aux[si], c_prev, dh, *carry);
+          gp[0] = r.di; gp[H] = r.df; gp[2 * H] = r.dg; gp[3 * H] = r.d_o;
+          *carry = r.dc_prev;
+        } else if constexpr (RNN == DS2_RNN_GRU) {
+          float h_prev = pin ? a.hseq[sp] : 0.f;
+          dh += *carry;
+          GruBwd r = gru_cell_bwd(gp[0], gp[H], gp[2 * H], a.aux[si], h_prev, dh);
+          gp[0] = r.dr; gp[H] = r.dz; gp[2 * H] = r.dxn;
+          a.aux[si] = r.dhn;
+          *carry = r.dh_prev;
+        } else {
+          float h = a.hseq[si];
+          gp[0] = dh * (1.f - h * h);
+        }
+      }
+    }
+  }
+}
+
+__global__ void sum_dirs_kernel(size_t n, int D, const float* __restrict__ hseq, float* __restrict__ y) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] = D == 2 ? hseq[i] + hseq[n + i] : hseq[i];
+}
+
+// hn[d,b,u] = state after the last valid step (fwd: t=len-1, reverse: t=0); h0 when len == 0
+__global__ void final_state_kernel(int T, int B, int H, int D, const int32_t* __restrict__ len,
+                                   const float* __restrict__ seq, const float* __restrict__ init,
+                                   float* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)D * B * H) return;
+  int u = (int)(i % H), b = (int)((i / H) % B), d = (int)(i / ((size_t)H * B));
+  int L = min(len[b], T);
+  float v;
+  if (L <= 0) v = init ? init[i] : 0.f;
+  else v = seq[(((size_t)d * T + (d == 0 ? L - 1 : 0)) * B + b) * H + u];
+  out[i] = v;
+}
+
+// dst[f] = sum_r src[r*ld + f]   (dst zeroed by the caller); grid (ceil(F/32), chunks), block (32,8)
+__global__ void colsum_strided_kernel(int rows, int F, const float* __restrict__ src, size_t ld,
+                                      float* __restrict__ dst) {
+  __shared__ float red[8][33];
+  int f = blockIdx.x * 32 + threadIdx.x;
+  int per = cdiv_dev(rows, gridDim.y), r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  float acc = 0.f;
+  if (f < F)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += src[(size_t)r * ld + f];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && f < F) {
+    for (int i = 1; i < 8; ++i) acc += red[i][threadIdx.x];
+    atomicAdd(&dst[f], acc);
+  }
+}
+
+// out (C, R) = in (R, C)^T
+__global__ void transpose_kernel(int R, int C, const float* __restrict__ in, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8)
+    if (r0 + j < R && c < C) tile[j][threadIdx.x] = in[(size_t)(r0 + j) * C + c];
+  __syncthreads();
+  int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += 8)
+    if (c0 + j < C && r < R) out[(size_t)(c0 + j) * R + r] = tile[threadIdx.x][j];
+}
+
+int transpose(int R, int C, const float* in, float* out, cudaStream_t st) {
+  DS2_LAUNCH(transpose_kernel, dim3(cdiv(C, 32), cdiv(R, 32)), dim3(32, 8), 0, st, R, C, in, out);
+  return DS2_OK;
+}
+
+static int colsum(int rows, int F, const float* src, size_t ld, float* dst, cudaStream_t st) {
+  DS2_CHECK_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * F, st));
+  int chunks = rows / 256;
+  chunks = chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks);
+  DS2_LAUNCH(colsum_strided_kernel, dim3(cdiv(F, 32), chunks), dim3(32, 8), 0, st, rows, F, src, ld, dst);
+  return DS2_OK;
+}
+
+static inline int num_gates(int rnn) { return rnn == DS2_RNN_LSTM ? 4 : (rnn == DS2_RNN_GRU ? 3 : 1); }
+
+struct Reserve {
+  float *gates, *hseq, *aux, *bnstats;
+  size_t total;
+};
+static Reserve carve_reserve(const ds2_rnn_desc* d, float* base) {
+  const size_t D = d->bidirectional ? 2 : 1, G = num_gates(d->rnn_type);
+  const size_t TB = (size_t)d->T * d->B;
+  Reserve r;
+  size_t off = 0;
+  r.gates = base + off; off += TB * D * G * d->H;
+  r.hseq = base + off; off += D * TB * d->H;
+  if (d->rnn_type != DS2_RNN_TANH) { r.aux = base + off; off += D * TB * d->H; } else r.aux = nullptr;
+  r.bnstats = base + off; off += 2 * (size_t)d->In;
+  r.total = off;
+  return r;
+}
+
+// tcgen05 persistent sweeps (rnn_persistent_tc.cu).  Return 1 when the shape is not eligible.
+int rnn_sweep_fwd_tc(int rnn, const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st);
+int rnn_sweep_bwd_tc(int rnn, const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t rnn_sweep_tc_workspace_bytes(int rnn, int T, int B, int H, int D);
+
+static int sweep_fwd(int rnn, const SeqArgs& a, cudaStream_t st) {
+  dim3 grid(cdiv(a.H, UT), a.D), block(32, UT);
+  for (int s = 0; s < a.T; ++s) {
+    if (rnn == DS2_RNN_LSTM) DS2_LAUNCH(rnn_step_fwd_kernel<DS2_RNN_LSTM>, grid, block, 0, st, a, s);
+    else if (rnn == DS2_RNN_GRU) DS2_LAUNCH(rnn_step_fwd_kernel<DS2_RNN_GRU>, grid, block, 0, st, a, s);
+    else DS2_LAUNCH(rnn_step_fwd_kernel<DS2_RNN_TANH>, grid, block, 0, st, a, s);
+  }
+  return DS2_OK;
+}
+static int sweep_bwd(int rnn, const SeqArgs& a, cudaStream_t st) {
+  dim3 grid(cdiv(a.H, UT), a.D), block(32, UT);
+  for (int s = 0; s < a.T; ++s) {
+    if (rnn == DS2_RNN_LSTM) DS2_LAUNCH(rnn_step_bwd_kernel<DS2_RNN_LSTM>, grid, block, 0, st, a, s);
+    else if (rnn == DS2_RNN_GRU) DS2_LAUNCH(rnn_step_bwd_kernel<DS2_RNN_GRU>, grid, block, 0, st, a, s);
+    else DS2_LAUNCH(rnn_step_bwd_kernel<DS2_RNN_TANH>, grid, block, 0, st, a, s);
+  }
+  return DS2_OK;
+}
+
+}  // namespace ds2
+
+extern "C" {
+using namespace ds2;
+
+size_t ds2_rnn_reserve_floats(const ds2_rnn_desc* d) {
+  if (!d) return 0;
+  return carve_reserve(d, nullptr).total;
+}
+
+size_t ds2_rnn_workspace_bytes(const ds2_rnn_desc* d) {
+  if (!d) return 0;
+  const size_t D = d->bidirectional ? 2 : 1, G = num_gates(d->rnn_type);
+  const size_t TB = (size_t)d->T * d->B, GH = G * d->H;
+  size_t n = 0;
+  n += 3 * align_up(TB * d->In * 4, 256);                 // xbn, xhat, dxbn
+  n += align_up(2 * (size_t)d->In * 8, 256);              // BN double sums
+  n += D * align_up(GH * d->H * 4, 256);                  // W_hh^T per direction
+  n += align_up(D * (size_t)d->B * d->H * 4, 256);        // carry
+  n += rnn_sweep_tc_workspace_bytes(d->rnn_type, d->T, d->B, d->H, (int)D);
+  n += ds2_gemm_workspace_bytes(1, 0, (int)GH, d->In > d->H ? d->In : d->H, (int)TB);
+  return n + 4096;
+}
+
+static int check_desc(const ds2_rnn_desc* d) {
+  DS2_REQUIRE(d, "rnn: null descriptor");
+  DS2_REQUIRE(d->rnn_type >= DS2_RNN_LSTM && d->rnn_type <= DS2_RNN_TANH, "rnn: unknown rnn_type %d", d->rnn_type);
+  DS2_REQUIRE(d->T > 0 && d->B > 0 && d->In > 0 && d->H > 0, "rnn: bad shape T=%d B=%d In=%d H=%d", d->T, d->B,
+              d->In, d->H);
+  return DS2_OK;
+}
+
+int ds2_rnn_layer_fwd(const ds2_rnn_desc* d, const float* x, const int32_t* len, const float* bn_gamma,
+                      const float* bn_beta, float* bn_rmean, float* bn_rvar, const float* const* w_ih,
+                      const float* const* w_hh, const float* const* b_ih, const float* const* b_hh, const float* h0,
+                      const float* c0, float* y, float* hn, float* cn, float* reserve, void* ws, size_t ws_bytes,
+                      void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  DS2_REQUIRE(ws_bytes >= ds2_rnn_workspace_bytes(d), "rnn fwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int D = d->bidirectional ? 2 : 1, G = num_gates(d->rnn_type), T = d->T, B = d->B, In = d->In, H = d->H;
+  const int TB = T * B, GH = G * H;
+  Reserve R = carve_reserve(d, reserve);
+  Arena ar(ws, ws_bytes);
+  const float* xin = x;
+  if (bn_gamma) {
+    float* xbn = ar.take<float>((size_t)TB * In);
+    double* sums = ar.take<double>(2 * (size_t)In);
+    rc = bn_rows_fwd(TB, In, x, bn_gamma, bn_beta, bn_rmean, bn_rvar, d->training, d->bn_momentum, d->bn_eps, xbn,
+                     nullptr, R.bnstats, sums, st);
+    if (rc) return rc;
+    xin = xbn;
+  }
+  void* gws = ar.base + ar.off;
+  size_t gws_bytes = ar.cap - ar.off;
+  // input projection for every time step and both directions: gates[:, d*GH:(d+1)*GH] = xin . W_ih[d]^T
+  for (int dir = 0; dir < D; ++dir) {
+    rc = ds2_gemm(0, 1, TB, GH, In, 1.f, xin, In, w_ih[dir], In, 0.f, R.gates + (size_t)dir * GH, D * GH, gws,
+                  gws_bytes, stream);
+    if (rc) return rc;
+  }
+  SeqArgs a{};
+  a.T = T; a.B = B; a.H = H; a.D = D; a.G = G; a.len = len;
+  a.gates = R.gates; a.hseq = R.hseq; a.aux = R.aux;
+  for (int dir = 0; dir < D; ++dir) { a.w_hh[dir] = w_hh[dir]; a.b_ih[dir] = b_ih[dir]; a.b_hh[dir] = b_hh[dir]; }
+  a.h0 = h0; a.c0 = c0; a.training = d->training;
+  rc = 1;
+  if (precision() == DS2_PREC_TF32) rc = rnn_sweep_fwd_tc(d->rnn_type, a, gws, gws_bytes, st);
+  if (rc == 1) rc = sweep_fwd(d->rnn_type, a, st);
+  if (rc) return rc;
+  size_t n = (size_t)TB * H;
+  int blocks = (int)((n + 1023) / 1024);
+  blocks = blocks > 148 * 16 ? 148 * 16 : blocks;
+  DS2_LAUNCH(sum_dirs_kernel, blocks, 256, 0, st, n, D, R.hseq, y);
+  if (hn) DS2_LAUNCH(final_state_kernel, cdiv((long long)D * B * H, 256), 256, 0, st, T, B, H, D, len, R.hseq, h0, hn);
+  if (cn && d->rnn_type == DS2_RNN_LSTM)
+    DS2_LAUNCH(final_state_kernel, cdiv((long long)D * B * H, 256), 256, 0, st, T, B, H, D, len, R.aux, c0, cn);
+  return DS2_OK;
+}
+
+int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len, const float* bn_gamma,
+                      const float* bn_beta, const float* const* w_ih, const float* const* w_hh,
+                      const float* const* b_ih, const float* const* b_hh, const float* dy, float* reserve, float* dx,
+                      float* dbn_gamma, float* dbn_beta, float* const* dw_ih, float* const* dw_hh,
+                      float* const* db_ih, float* const* db_hh, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  DS2_REQUIRE(ws_bytes >= ds2_rnn_workspace_bytes(d), "rnn bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int D = d->bidirectional ? 2 : 1, G = num_gates(d->rnn_type), T = d->T, B = d->B, In = d->In, H = d->H;
+  const int TB = T * B, GH = G * H;
+  Reserve R = carve_reserve(d, reserve);
+  Arena ar(ws, ws_bytes);
+  float *xbn = nullptr, *xhat = nullptr, *dxbn = nullptr;
+  double* sums = nullptr;
+  if (bn_gamma) {
+    xbn = ar.take<float>((size_t)TB * In);
+    xhat = ar.take<float>((size_t)TB * In);
+    dxbn = ar.take<float>((size_t)TB * In);
+    sums = ar.take<double>(2 * (size_t)In);
+  }
+  float* wT[2] = {nullptr, nullptr};
+  for (int dir = 0; dir < D; ++dir) wT[dir] = ar.take<float>((size_t)GH * H);
+  float* carry = ar.take<float>((size_t)D * B * H);
+  void* gws = ar.base + ar.off;
+  size_t gws_bytes = ar.cap - ar.off;
+
+  for (int dir = 0; dir < D; ++dir) {
+    rc = transpose(GH, H, w_hh[dir], wT[dir], st);
+    if (rc) return rc;
+  }
+  DS2_CHECK_CUDA(cudaMemsetAsync(carry, 0, sizeof(float) * (size_t)D * B * H, st));
+  SeqArgs a{};
+  a.T = T; a.B = B; a.H = H; a.D = D; a.G = G; a.len = len;
+  a.gates = R.gates; a.hseq = R.hseq; a.aux = R.aux;
+  for (int dir = 0; dir < D; ++dir) { a.w_hh[dir] = wT[dir]; a.b_ih[dir] = b_ih[dir]; a.b_hh[dir] = b_hh[dir]; }
+  a.dy = dy; a.carry = carry; a.training = 1;
+  rc = 1;
+  if (precision() == DS2_PREC_TF32) rc = rnn_sweep_bwd_tc(d->rnn_type, a, gws, gws_bytes, st);
+  if (rc == 1) rc = sweep_bwd(d->rnn_type, a, st);
+  if (rc) return rc;
+
+  // the layer input as the projection saw it (BN applied) and its normalised form for the BN backward
+  const float* xin = x;
+  if (bn_gamma) {
+    // recompute xhat and xbn from the saved batch statistics
+    rc = bn_rows_reapply(TB, In, x, bn_gamma, bn_beta, R.bnstats, xbn, xhat, st);
+    if (rc) return rc;
+    xin = xbn;
+  }
+  const bool gru = d->rnn_type == DS2_RNN_GRU;
+  for (int dir = 0; dir < D; ++dir) {
+    const float* dG = R.gates + (size_t)dir * GH;   // (TB, GH) with row stride D*GH : dGx
+    const int ldg = D * GH;
+    const float* aux_d = R.aux ? R.aux + (size_t)dir * TB * H : nullptr;   // GRU: dGh_n (TB,H)
+    const float* hseq_d = R.hseq + (size_t)dir * TB * H;
+    // dW_ih = dGx^T . xin
+    rc = ds2_gemm(1, 0, GH, In, TB, 1.f, dG, ldg, xin, In, 0.f, dw_ih[dir], In, gws, gws_bytes, stream);
+    if (rc) return rc;
+    rc = colsum(TB, GH, dG, ldg, db_ih[dir], st);
+    if (rc) return rc;
+    // dW_hh = sum_t dGh[t]^T . h_prev[t]; h_prev[t] = hseq[t-1] (forward) / hseq[t+1] (reverse)
+    const int Kr = (T - 1) * B;
+    const size_t a_off = dir == 0 ? (size_t)B : 0, h_off = dir == 0 ? 0 : (size_t)B;
+    const int rows_x = gru ? 2 * H : GH;   // rows whose dGh == dGx
+    if (Kr > 0) {
+      rc = ds2_gemm(1, 0, rows_x, H, Kr, 1.f, dG + a_off * ldg, ldg, hseq_d + h_off * H, H, 0.f, dw_hh[dir], H, gws,
+                    gws_bytes, stream);
+      if (rc) return rc;
+      if (gru) {
+        rc = ds2_gemm(1, 0, H, H, Kr, 1.f, aux_d + a_off * H, H, hseq_d + h_off * H, H, 0.f,
+                      dw_hh[dir] + (size_t)2 * H * H, H, gws, gws_bytes, stream);
+        if (rc) return rc;
+      }
+    } else {
+      DS2_CHECK_CUDA(cudaMemsetAsync(dw_hh[dir], 0, sizeof(float) * (size_t)GH * H, st));
+    }
+    if (gru) {
+      DS2_CHECK_CUDA(cudaMemcpyAsync(db_hh[dir], db_ih[dir], sizeof(float) * 2 * H, cudaMemcpyDeviceToDevice, st));
+      rc = colsum(TB, H, aux_d, H, db_hh[dir] + 2 * H, st);
+      if (rc) return rc;
+    } else {
+      DS2_CHECK_CUDA(cudaMemcpyAsync(db_hh[dir], db_ih[dir], sizeof(float) * GH, cudaMemcpyDeviceToDevice, st));
+    }
+    // dX (pre-BN-affine) += dGx . W_ih
+    if (dx) {
+      rc = ds2_gemm(0, 0, TB, In, GH, 1.f, dG, ldg, w_ih[dir], In, dir == 0 ? 0.f : 1.f, bn_gamma ? dxbn : dx, In,
+                    gws, gws_bytes, stream);
+      if (rc) return rc;
+    }
+  }
+  if (bn_gamma) {
+    DS2_REQUIRE(dx && dbn_gamma && dbn_beta, "rnn bwd: BN layer needs dx, dbn_gamma, dbn_beta");
+    rc = bn_rows_bwd(TB, In, xhat, bn_gamma, R.bnstats, dxbn, dx, dbn_gamma, dbn_beta, sums, st);
+    if (rc) return rc;
+  }
+  return DS2_OK;
+}
+
+}  // extern "C"

