@@ -96,6 +96,7 @@ int bn_rows_fwd(int rows, int F, const float* x, const float* gamma, const float
 int bn_rows_reapply(int rows, int F, const float* x, const float* gamma, const float* beta,
                     const float* mean_invstd, float* y, float* xhat, cudaStream_t st);
 int transpose(int R, int C, const float* in, float* out, cudaStream_t st);
+int transpose_strided(int R, int C, const float* in, size_t ldi, float* out, size_t ldo, cudaStream_t st);
 // dx = gamma*invstd*(dy - mean(dy) - xhat*mean(dy*xhat)); dgamma, dbeta written.
 int bn_rows_bwd(int rows, int F, const float* xhat, const float* gamma, const float* mean_invstd, const float* dy,
                 float* dx, float* dgamma, float* dbeta, double* ws_sums /*2F doubles*/, cudaStream_t st);

@@ -37,92 +37,98 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
 }
 
 // grid (B, 2); dynamic smem: int ext[Smax] + float buf[2][Smax + 2]
+// blockIdx.y = 0: alpha sweep, 1: beta sweep.  The beta recursion is the alpha recursion on the
+// mirrored problem (states r = S-1-s, time reversed), so both run the same code.
+// Scaled recursion: every RESCALE steps the block maximum is subtracted from all states and
+// accumulated (in double) into a per-time offset, so the fp32 log-values stay O(10) instead of
+// O(-nll) and keep ~1e-6 absolute precision: table[t][s] + offs[t] = log alpha_t(s).
+constexpr int RESCALE = 8;
+
 __global__ void ctc_alpha_beta_kernel(int T, int B, int C, int Smax, const float* __restrict__ lp,
                                       const int64_t* __restrict__ targets, const int32_t* __restrict__ in_len,
                                       const int32_t* __restrict__ tgt_len, int blank, float* __restrict__ alpha,
-                                      float* __restrict__ beta, float* __restrict__ loglik) {
+                                      float* __restrict__ beta, double* __restrict__ offs_a,
+                                      double* __restrict__ offs_b, double* __restrict__ loglik) {
   extern __shared__ unsigned char smem_raw[];
-  int* ext = reinterpret_cast<int*>(smem_raw);
+  int* ext = reinterpret_cast<int*>(smem_raw);           // mirrored for the beta sweep
   float* buf = reinterpret_cast<float*>(ext + Smax);
+  __shared__ float wmax[32];
+  __shared__ long long off_s;
+  __shared__ double shift_s;
   const int b = blockIdx.x;
   const bool is_beta = blockIdx.y == 1;
   const int Tb = in_len[b], Lb = tgt_len[b];
   const int S = 2 * Lb + 1;
-  __shared__ long long off_s;
   if (threadIdx.x == 0) {
     long long off = 0;
     for (int i = 0; i < b; ++i) off += tgt_len[i];
     off_s = off;
+    shift_s = 0.0;
   }
   __syncthreads();
-  for (int s = threadIdx.x; s < S; s += blockDim.x) ext[s] = (s & 1) ? (int)targets[off_s + (s >> 1)] : blank;
+  for (int r = threadIdx.x; r < S; r += blockDim.x) {
+    int s = is_beta ? S - 1 - r : r;
+    ext[r] = (s & 1) ? (int)targets[off_s + (s >> 1)] : blank;
+  }
   const int W = Smax + 2;  // buffer row: [0,1] = -inf guards, states at [2, 2+S)
   for (int i = threadIdx.x; i < 2 * W; i += blockDim.x) buf[i] = -CUDART_INF_F;
   __syncthreads();
   if (Tb <= 0) {
-    if (!is_beta && threadIdx.x == 0) loglik[b] = (Lb == 0) ? 0.f : -CUDART_INF_F;
+    if (!is_beta && threadIdx.x == 0) loglik[b] = (Lb == 0) ? 0.0 : -(double)CUDART_INF_F;
     return;
   }
   float* table = (is_beta ? beta : alpha) + (size_t)b * T * Smax;
+  double* offs = (is_beta ? offs_b : offs_a) + (size_t)b * T;
   const size_t row_stride = (size_t)B * C;
   const float* lpb = lp + (size_t)b * C;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nwarps = blockDim.x / 32;
 
-  if (!is_beta) {
-    // alpha_0
-    for (int s = threadIdx.x; s < S; s += blockDim.x) {
-      float v = (s < 2) ? lpb[ext[s]] : -CUDART_INF_F;
-      buf[2 + s] = v;
-      table[s] = v;
-    }
-    __syncthreads();
-    int cur = 0;
-    for (int t = 1; t < Tb; ++t) {
-      const float* prev = buf + cur * W + 2;
-      float* next = buf + (cur ^ 1) * W + 2;
-      const float* lpt = lpb + (size_t)t * row_stride;
-      for (int s = threadIdx.x; s < S; s += blockDim.x) {
-        int l = ext[s];
-        bool skip = (s >= 2) && (l != blank) && (l != ext[s - 2]);
-        float a2 = skip ? prev[s - 2] : -CUDART_INF_F;
-        float v = lse3(prev[s], prev[s - 1], a2) + lpt[l];   // prev[-1], prev[-2] are the -inf guards
-        next[s] = v;
-        table[(size_t)t * Smax + s] = v;
+  int cur = 0;
+  for (int tt = 0; tt < Tb; ++tt) {
+    const int t = is_beta ? Tb - 1 - tt : tt;
+    const float* prev = buf + cur * W + 2;
+    float* next = buf + (cur ^ 1) * W + 2;
+    const float* lpt = lpb + (size_t)t * row_stride;
+    float local_max = -CUDART_INF_F;
+    for (int r = threadIdx.x; r < S; r += blockDim.x) {
+      const int l = ext[r];
+      float v;
+      if (tt == 0) {
+        v = (r < 2) ? lpt[l] : -CUDART_INF_F;
+      } else {
+        bool skip = (r >= 2) && (l != blank) && (l != ext[r - 2]);
+        float a2 = skip ? prev[r - 2] : -CUDART_INF_F;
+        v = lse3(prev[r], prev[r - 1], a2) + lpt[l];      // prev[-1], prev[-2] are the -inf guards
       }
+      next[r] = v;
+      local_max = fmaxf(local_max, v);
+    }
+    if ((tt % RESCALE) == RESCALE - 1) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) local_max = fmaxf(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+      if (lane == 0) wmax[warp] = local_max;
       __syncthreads();
-      cur ^= 1;
-    }
-    if (threadIdx.x == 0) {
-      const float* last = buf + cur * W + 2;
-      float a = last[S - 1], c = (S > 1) ? last[S - 2] : -CUDART_INF_F;
-      float m = fmaxf(a, c);
-      loglik[b] = (m == -CUDART_INF_F) ? -CUDART_INF_F : m + logf(expf(a - m) + expf(c - m));
-    }
-  } else {
-    // beta_{Tb-1}; guards live past the end: use mirrored indexing r = S-1-s so guards are again at -1,-2
-    const float* lpt0 = lpb + (size_t)(Tb - 1) * row_stride;
-    for (int s = threadIdx.x; s < S; s += blockDim.x) {
-      float v = (s >= S - 2) ? lpt0[ext[s]] : -CUDART_INF_F;
-      buf[2 + (S - 1 - s)] = v;
-      table[(size_t)(Tb - 1) * Smax + s] = v;
-    }
-    __syncthreads();
-    int cur = 0;
-    for (int t = Tb - 2; t >= 0; --t) {
-      const float* prev = buf + cur * W + 2;
-      float* next = buf + (cur ^ 1) * W + 2;
-      const float* lpt = lpb + (size_t)t * row_stride;
-      for (int s = threadIdx.x; s < S; s += blockDim.x) {
-        int l = ext[s];
-        int r = S - 1 - s;
-        bool skip = (s + 2 < S) && (ext[s + 2] != blank) && (ext[s + 2] != l);
-        float b2 = skip ? prev[r - 2] : -CUDART_INF_F;
-        float v = lse3(prev[r], prev[r - 1], b2) + lpt[l];
-        next[r] = v;
-        table[(size_t)t * Smax + s] = v;
+      float m = -CUDART_INF_F;
+      for (int w = 0; w < nwarps; ++w) m = fmaxf(m, wmax[w]);
+      if (m != -CUDART_INF_F) {
+        for (int r = threadIdx.x; r < S; r += blockDim.x) next[r] -= m;   // own states only
+        if (threadIdx.x == 0) shift_s += (double)m;
       }
-      __syncthreads();
-      cur ^= 1;
     }
+    for (int r = threadIdx.x; r < S; r += blockDim.x) {
+      int s = is_beta ? S - 1 - r : r;
+      table[(size_t)t * Smax + s] = next[r];
+    }
+    if (threadIdx.x == 0) offs[t] = shift_s;
+    __syncthreads();
+    cur ^= 1;
+  }
+  if (!is_beta && threadIdx.x == 0) {
+    const float* last = buf + cur * W + 2;
+    float a = last[S - 1], c = (S > 1) ? last[S - 2] : -CUDART_INF_F;
+    float m = fmaxf(a, c);
+    loglik[b] = (m == -CUDART_INF_F) ? -(double)CUDART_INF_F
+                                      : shift_s + (double)m + log((double)expf(a - m) + (double)expf(c - m));
   }
 }
 
@@ -131,7 +137,9 @@ __global__ void ctc_grad_kernel(int T, int B, int C, int Smax, const float* __re
                                 const int64_t* __restrict__ targets, const int32_t* __restrict__ in_len,
                                 const int32_t* __restrict__ tgt_len, const long long* __restrict__ tgt_off,
                                 int blank, const float* __restrict__ alpha, const float* __restrict__ beta,
-                                const float* __restrict__ loglik, float* __restrict__ nll, float* __restrict__ grad) {
+                                const double* __restrict__ offs_a, const double* __restrict__ offs_b,
+                                const double* __restrict__ loglik, float* __restrict__ nll,
+                                float* __restrict__ grad) {
   extern __shared__ float post_all[];  // warps_per_block * Cpad
   const int wpb = blockDim.x / 32;
   const int w = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -141,10 +149,11 @@ __global__ void ctc_grad_kernel(int T, int B, int C, int Smax, const float* __re
   if (idx >= (long long)T * B) return;
   int t = (int)(idx / B), b = (int)(idx % B);
   float* g = grad + ((size_t)t * B + b) * C;
-  const float ll = loglik[b];
+  const double ll = loglik[b];
+  const bool feasible = ll > -1e300;
   const int Tb = in_len[b];
-  if (t == 0 && lane == 0) nll[b] = (ll == -CUDART_INF_F) ? 0.f : -ll;  // zero_infinity
-  if (t >= Tb || ll == -CUDART_INF_F) {
+  if (t == 0 && lane == 0) nll[b] = feasible ? (float)(-ll) : 0.f;  // zero_infinity
+  if (t >= Tb || !feasible) {
     for (int c = lane; c < C; c += 32) g[c] = 0.f;
     return;
   }
@@ -155,10 +164,12 @@ __global__ void ctc_grad_kernel(int T, int B, int C, int Smax, const float* __re
   const float* be = beta + ((size_t)b * T + t) * Smax;
   const float* lpr = lp + ((size_t)t * B + b) * C;
   const int64_t* tg = targets + tgt_off[b];
+  // log posterior(s) = alpha + beta - lp - ll, with the big scalars combined in double first
+  const float kt = (float)(offs_a[(size_t)b * T + t] + offs_b[(size_t)b * T + t] - ll);
   for (int s = lane; s < S; s += 32) {
     int l = (s & 1) ? (int)tg[s >> 1] : blank;
     float v = a[s] + be[s];
-    if (v != -CUDART_INF_F) atomicAdd(&post[l], expf(v - lpr[l] - ll));
+    if (v != -CUDART_INF_F) atomicAdd(&post[l], expf(v - lpr[l] + kt));
   }
   __syncwarp();
   for (int c = lane; c < C; c += 32) g[c] = expf(lpr[c]) - post[c];
@@ -179,7 +190,8 @@ size_t ds2_ctc_workspace_bytes(int T, int B, int C, int max_tgt_len) {
   size_t Smax = 2 * (size_t)max_tgt_len + 1;
   size_t n = ds2::align_up((size_t)T * B * C * 4, 256)      // lp
              + 2 * ds2::align_up((size_t)B * T * Smax * 4, 256)  // alpha, beta
-             + ds2::align_up((size_t)B * 4, 256)                 // loglik
+             + 2 * ds2::align_up((size_t)B * T * 8, 256)         // per-time scale offsets (double)
+             + ds2::align_up((size_t)B * 8, 256)                 // loglik (double)
              + ds2::align_up((size_t)B * 8, 256);                // target offsets
   return n;
 }
@@ -196,9 +208,11 @@ int ds2_ctc_loss_fwd_bwd(int T, int B, int C, const float* logits, const int64_t
   float* lp = ar.take<float>((size_t)T * B * C);
   float* alpha = ar.take<float>((size_t)B * T * Smax);
   float* beta = ar.take<float>((size_t)B * T * Smax);
-  float* loglik = ar.take<float>(B);
+  double* offs_a = ar.take<double>((size_t)B * T);
+  double* offs_b = ar.take<double>((size_t)B * T);
+  double* loglik = ar.take<double>(B);
   long long* off = ar.take<long long>(B);
-  if (!lp || !alpha || !beta || !loglik || !off) { set_error("ds2_ctc: arena"); return DS2_ERR_WORKSPACE; }
+  if (!lp || !alpha || !beta || !offs_a || !offs_b || !loglik || !off) { set_error("ds2_ctc: arena"); return DS2_ERR_WORKSPACE; }
 
   int rows = T * B;
   DS2_LAUNCH(ctc_logsoftmax_kernel, cdiv(rows, 8), 256, 0, st, rows, C, logits, lp);
@@ -210,11 +224,11 @@ int ds2_ctc_loss_fwd_bwd(int T, int B, int C, const float* logits, const int64_t
   if (smem > 48 * 1024)
     DS2_CHECK_CUDA(cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   DS2_LAUNCH(ctc_alpha_beta_kernel, dim3(B, 2), threads, smem, st, T, B, C, Smax, lp, targets, in_len, tgt_len, blank,
-             alpha, beta, loglik);
+             alpha, beta, offs_a, offs_b, loglik);
   const int wpb = 8;
   size_t smem3 = (size_t)wpb * ((C + 31) / 32 * 32) * 4;
   DS2_LAUNCH(ctc_grad_kernel, cdiv((long long)T * B, wpb), wpb * 32, smem3, st, T, B, C, Smax, lp, targets, in_len,
-             tgt_len, off, blank, alpha, beta, loglik, nll, grad);
+             tgt_len, off, blank, alpha, beta, offs_a, offs_b, loglik, nll, grad);
   return DS2_OK;
 }
 

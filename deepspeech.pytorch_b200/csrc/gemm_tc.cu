@@ -1,7 +1,256 @@
-// placeholder until the tcgen05 kernel lands
+// tcgen05 TF32 GEMM:  C[M,N] = alpha * A[M,K] . B[N,K]^T + beta * C   (both operands K-major).
+//
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles (128B swizzle) of A (128 x 32 fp32) and
+//               B (256 x 32 fp32) into a 4-stage shared-memory ring, mbarrier complete_tx signalling
+//   warp 1      allocates 256 TMEM columns, then one elected lane issues tcgen05.mma.kind::tf32
+//               (M=128, N=256, K=8) x4 per stage, accumulating in TMEM; tcgen05.commit frees the stage
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> alpha/beta -> global
+//
+// Operands that are not K-major in memory (transA / !transB) are first transposed into the
+// workspace by a tiled transpose kernel (a few % of the GEMM time at the shapes of this path).
+// Shapes the kernel does not take (tiny or unaligned) return 1 and the caller uses the FFMA GEMM.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tc_common.cuh"
+
 namespace ds2 {
-int gemm_tc(int, int, int, int, int, float, const float*, int, const float*, int, float, float*, int, void*, size_t,
-            cudaStream_t) { return 1; }
-size_t gemm_tc_workspace_bytes(int, int, int, int, int) { return 0; }
+
+// ---- tensor maps ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static CUtensorMapDataType g_tmap_dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+
+static int load_encode() {
+  if (g_encode) return DS2_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  DS2_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return DS2_ERR_CUDA;
+  }
+  const char* e = getenv("DS2_TMAP_TF32");   // experiment switch: let TMA convert fp32 -> tf32 on load
+  if (e && e[0] == '1') g_tmap_dtype = CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return DS2_OK;
 }
+
+int make_tmap_2d(CUtensorMap* out, const float* base, int rows, int cols, int ld, int box_rows, int box_cols) {
+  int rc = load_encode();
+  if (rc) return rc;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, g_tmap_dtype, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(2d rows=%d cols=%d ld=%d box=%dx%d base=%p) failed: %d", rows, cols, ld,
+              box_rows, box_cols, (const void*)base, (int)r);
+    return DS2_ERR_CUDA;
+  }
+  return DS2_OK;
+}
+
+int make_tmap_3d(CUtensorMap* out, const float* base, int d0, int d1, int d2, size_t stride1, size_t stride2,
+                 int box0, int box1, int box2) {
+  int rc = load_encode();
+  if (rc) return rc;
+  cuuint64_t gdim[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t gstr[2] = {(cuuint64_t)stride1 * sizeof(float), (cuuint64_t)stride2 * sizeof(float)};
+  cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, (cuuint32_t)box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(out, g_tmap_dtype, 3, const_cast<float*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d %d,%d,%d box %d,%d,%d) failed: %d", d0, d1, d2, box0, box1, box2, (int)r);
+    return DS2_ERR_CUDA;
+  }
+  return DS2_OK;
+}
+
+// ---- kernel ---------------------------------------------------------------------------------------
+namespace gtc {
+constexpr int BM = 128, BN = 256, BK = 32, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int THREADS = 192;
+}  // namespace gtc
+
+__global__ void __launch_bounds__(gtc::THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+               float alpha, float beta, float* __restrict__ C, int ldc) {
+  using namespace gtc;
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum_bar = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nk = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+        tma_load_2d(smem + s * STAGE_BYTES, &tmA, &full[s], kb * BK, m0);
+        tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &tmB, &full[s], kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc(FMT_TF32, BM, BN);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint64_t adesc = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES));
+        const uint64_t bdesc = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k)   // advance 32 bytes (8 tf32) inside the 128B swizzle row
+          mma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        mma_commit(&empty[s]);             // stage reusable when these MMAs have read it
+      }
+      mma_commit(accum_bar);               // accumulator complete
+    }
+  } else {
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int q = warp % 4;                // TMEM lane quarter this warp may read
+    const int row = m0 + q * 32 + lane;
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int col0 = n0 + c * 32;
+      if (col0 >= N) break;                // warp-uniform
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      if (row < M) {
+        float* cp = C + (size_t)row * ldc + col0;
+        if (vec_ok && col0 + 32 <= N) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(alpha * v[4 * j], alpha * v[4 * j + 1], alpha * v[4 * j + 2], alpha * v[4 * j + 3]);
+            if (beta != 0.f) {
+              float4 old = *reinterpret_cast<const float4*>(cp + 4 * j);
+              o.x = fmaf(beta, old.x, o.x); o.y = fmaf(beta, old.y, o.y);
+              o.z = fmaf(beta, old.z, o.z); o.w = fmaf(beta, old.w, o.w);
+            }
+            *reinterpret_cast<float4*>(cp + 4 * j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < N) {
+              float o = alpha * v[j];
+              if (beta != 0.f) o = fmaf(beta, cp[j], o);
+              cp[j] = o;
+            }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+}
+
+// out (C x R, pitch ldo) = in (R x C, pitch ldi)^T
+__global__ void transpose_strided_kernel(int R, int C, const float* __restrict__ in, size_t ldi,
+                                         float* __restrict__ out, size_t ldo) {
+  __shared__ float tile[32][33];
+  int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8)
+    if (r0 + j < R && c < C) tile[j][threadIdx.x] = in[(size_t)(r0 + j) * ldi + c];
+  __syncthreads();
+  int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += 8)
+    if (c0 + j < C && r < R) out[(size_t)(c0 + j) * ldo + r] = tile[threadIdx.x][j];
+}
+
+int transpose_strided(int R, int C, const float* in, size_t ldi, float* out, size_t ldo, cudaStream_t st) {
+  DS2_LAUNCH(transpose_strided_kernel, dim3(cdiv(C, 32), cdiv(R, 32)), dim3(32, 8), 0, st, R, C, in, ldi, out, ldo);
+  return DS2_OK;
+}
+int transpose(int R, int C, const float* in, float* out, cudaStream_t st) {
+  return transpose_strided(R, C, in, (size_t)C, out, (size_t)R, st);
+}
+
+static inline size_t k4(int K) { return (size_t)((K + 3) / 4 * 4); }
+
+size_t gemm_tc_workspace_bytes(int transA, int transB, int M, int N, int K) {
+  size_t n = 0;
+  if (transA) n += align_up((size_t)M * k4(K) * 4, 256);
+  if (!transB) n += align_up((size_t)N * k4(K) * 4, 256);
+  return n;
+}
+
+static bool tc_eligible(int M, int N, int K) { return K >= 32 && M >= 32 && N >= 16 && (long long)M * N * K >= (1 << 18); }
+
+int gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+            int ldb, float beta, float* C, int ldc, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!tc_eligible(M, N, K)) return 1;
+  Arena ar(ws, ws_bytes);
+  const float* Ak = A;
+  int ldak = lda;
+  if (transA) {  // stored (K, M) -> (M, K)
+    float* t = ar.take<float>((size_t)M * k4(K));
+    if (!t) return 1;
+    int rc = transpose_strided(K, M, A, (size_t)lda, t, k4(K), st);
+    if (rc) return rc;
+    Ak = t;
+    ldak = (int)k4(K);
+  }
+  const float* Bk = B;
+  int ldbk = ldb;
+  if (!transB) {  // stored (K, N) -> (N, K)
+    float* t = ar.take<float>((size_t)N * k4(K));
+    if (!t) return 1;
+    int rc = transpose_strided(K, N, B, (size_t)ldb, t, k4(K), st);
+    if (rc) return rc;
+    Bk = t;
+    ldbk = (int)k4(K);
+  }
+  if ((ldak & 3) || (ldbk & 3) || (reinterpret_cast<uintptr_t>(Ak) & 15) || (reinterpret_cast<uintptr_t>(Bk) & 15))
+    return 1;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(&tmA, Ak, M, K, ldak, gtc::BM, gtc::BK);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmB, Bk, N, K, ldbk, gtc::BN, gtc::BK);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DS2_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gtc::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(N, gtc::BN), cdiv(M, gtc::BM));
+  DS2_LAUNCH(gemm_tc_kernel, grid, gtc::THREADS, gtc::SMEM_BYTES, st, tmA, tmB, M, N, K, alpha, beta, C, ldc);
+  return DS2_OK;
+}
+
+}  // namespace ds2

@@ -230,23 +230,6 @@ __global__ void colsum_strided_kernel(int rows, int F, const float* __restrict__
   }
 }
 
-// out (C, R) = in (R, C)^T
-__global__ void transpose_kernel(int R, int C, const float* __restrict__ in, float* __restrict__ out) {
-  __shared__ float tile[32][33];
-  int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
-  for (int j = threadIdx.y; j < 32; j += 8)
-    if (r0 + j < R && c < C) tile[j][threadIdx.x] = in[(size_t)(r0 + j) * C + c];
-  __syncthreads();
-  int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
-  for (int j = threadIdx.y; j < 32; j += 8)
-    if (c0 + j < C && r < R) out[(size_t)(c0 + j) * R + r] = tile[threadIdx.x][j];
-}
-
-int transpose(int R, int C, const float* in, float* out, cudaStream_t st) {
-  DS2_LAUNCH(transpose_kernel, dim3(cdiv(C, 32), cdiv(R, 32)), dim3(32, 8), 0, st, R, C, in, out);
-  return DS2_OK;
-}
-
 static int colsum(int rows, int F, const float* src, size_t ld, float* dst, cudaStream_t st) {
   DS2_CHECK_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * F, st));
   int chunks = rows / 256;
