@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Benchmark of the DeepSpeech2 train step (BASELINE.json metric: utterances/sec, 161x1000 synthetic
+spectrograms).  One JSON line on stdout (rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = forward + CTC + backward (+ one gradient all-reduce for N>1) + fused clip/AdamW step on one
+batch of B=32 utterances per GPU (weak scaling).  `value` is timed with the batch resident in HBM;
+`e2e` repeats the same steps through the public API with pinned-host inputs copied H2D and the loss
+read back D2H inside the timed region.  `--impl reference` times the reference's own CPU path (the
+oracle port issuing the same ATen calls: oneDNN conv, packed `_VF.lstm`, `ctc_loss`, autograd) on the
+host cores of the box, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: rnn_type, bidirectional, H, layers, ctx, B/GPU, T, target_len     (BASELINE.json configs)
+    "librispeech": ("lstm", True, 1024, 5, 20, 32, 1000, 200),      # configs[1] / [2]: the headline
+    "an4": ("gru", True, 256, 2, 20, 4, 1000, 200),                 # configs[0]
+    "unigru_lookahead": ("gru", False, 1024, 5, 20, 32, 1000, 200),  # configs[3]
+    "stress": ("lstm", True, 1536, 7, 20, 8, 4000, 400),            # configs[4]
+}
+
+
+T0 = time.time()
+
+
+def log(msg):
+    print(f"[bench +{time.time() - T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port, ATen ops) on the host."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import ds2_oracle as O
+    rnn, bidir, H, layers, ctx, B, T, L = WORKLOADS[args.workload]
+    cores = host_cores()
+    torch.set_num_threads(cores)
+    Bs = args.cpu_batch
+    ocfg = O.OracleConfig(rnn_type=rnn, hidden_size=H, hidden_layers=layers, bidirectional=bidir,
+                          lookahead_context=ctx)
+    P = O.init_params(ocfg, seed=123456)
+    x, targets, pct, tsz = O.synth_batch(Bs, T, seed=1234, ragged=False, lmin=L, lmax=L)
+
+    def step():
+        O.train_step(x, targets, pct.clone(), tsz, P, ocfg, use_aten_rnn=True, use_aten_ctc=True)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    v = Bs / dt
+    line = {"impl": "reference", "metric": "utterances/sec (train step, 161x1000 spectrogram)", "value": v,
+            "unit": "utt/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "rnn": f"{layers}x{'bi' if bidir else 'uni'}-{rnn}-{H}",
+                       "frames": T, "target_len": L, "batch_per_step": Bs},
+            "cpu_baseline": {"value": v, "unit": "utt/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} steps of B={Bs} utterances (fwd+CTC+bwd, torch CPU ATen ops, "
+                                       f"{cores} threads)"},
+            "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_baseline(workload, timeout_s=150):
+    """reference CPU path (oracle port) on a bounded sample, in a subprocess so that a slow host cannot stall
+    the bench: 1 warm-up + 2 timed steps of B=2 utterances of the same workload."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload, "--steps", "2",
+           "--warmup", "1", "--cpu-batch", "2"]
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env).stdout.strip().splitlines()
+        d = json.loads(out[-1])["cpu_baseline"]
+        return d
+    except subprocess.TimeoutExpired:
+        return {"value": None, "unit": "utt/s", "cores": host_cores(), "kind": "port",
+                "sample": f"did not finish 3 steps of B=2 within {timeout_s} s"}
+    except Exception as e:  # pragma: no cover
+        return {"value": None, "unit": "utt/s", "cores": host_cores(), "kind": "port", "sample": f"failed: {e!r}"}
+
+
+def stock_cuda_baseline(workload, steps=5, warmup=2):
+    """north_star's denominator: the reference's stock PyTorch CUDA path (cuDNN conv/RNN with TF32 allowed,
+    ATen CTC, torch AdamW) — same ATen calls as reference model.py, issued by the oracle port on the GPU."""
+    import torch
+    from oracle import ds2_oracle as O
+    rnn, bidir, H, layers, ctx, B, T, L = WORKLOADS[workload]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ocfg = O.OracleConfig(rnn_type=rnn, hidden_size=H, hidden_layers=layers, bidirectional=bidir,
+                          lookahead_context=ctx)
+    P = {k: v.to(dev) for k, v in O.init_params(ocfg, seed=123456).items()}
+    leaves = {k: v.clone().requires_grad_(True) for k, v in P.items() if v.dtype.is_floating_point and "running_" not in k}
+    opt = torch.optim.AdamW(list(leaves.values()), lr=1.5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
+    x, targets, pct, tsz = O.synth_batch(B, T, seed=1234, ragged=False, lmin=L, lmax=L)
+    x = x.to(dev)
+    import torch.nn.functional as F
+
+    def step():
+        Q = dict(P)
+        Q.update(leaves)
+        sizes = O.input_sizes_from_percentages(pct, T)
+        out, osz, _, _ = O.forward(x, sizes, Q, ocfg, training=True, use_aten_rnn=True)
+        loss = F.ctc_loss(out.transpose(0, 1).log_softmax(-1), targets, osz, tsz, blank=0, reduction="sum",
+                          zero_infinity=True)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(leaves.values()), 400.0)
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": B / (ms * 1e-3), "unit": "utt/s", "ms_per_step": ms, "kind": "stock torch CUDA ops (cuDNN TF32 "
+            "conv/RNN, ATen CTC, torch AdamW) issued by the oracle port", "steps": steps}
+
+
+def run_b200(args):
+    import torch
+    import deepspeech_pytorch_b200 as ds
+    from deepspeech_pytorch_b200 import dist as D
+    from deepspeech_pytorch_b200.optim import FlatParams, FusedOptimizer
+    from oracle import ds2_oracle as O   # synthetic batch generator + cpu_baseline leg only
+
+    rank, world, local = D.init_from_env()
+    assert torch.cuda.is_available(), "bench.py (impl b200) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = ds.get_lib()
+    ds.set_precision(args.precision)
+    rnn, bidir, H, layers, ctx, B, T, L = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    rt = getattr(ds.RNNType, rnn)
+    mcfg = (ds.BiDirectionalConfig(rnn_type=rt, hidden_size=H, hidden_layers=layers) if bidir else
+            ds.UniDirectionalConfig(rnn_type=rt, hidden_size=H, hidden_layers=layers, lookahead_context=ctx))
+    torch.manual_seed(123456)
+    model = ds.DeepSpeech(ds.LABELS, mcfg, 32, ds.AdamConfig(), ds.SpectConfig()).to(dev).train()
+    flat = FlatParams(model)
+    opt = FusedOptimizer(flat, model.optim_cfg, max_norm=400.0)
+    n_params = sum(p.numel() for p in model.parameters())
+
+    x, targets, pct, tsz = O.synth_batch(B, T, seed=1234 + rank, ragged=False, lmin=L, lmax=L)
+    x_pinned = x.pin_memory()
+    x_dev = x.to(dev)
+    targets_pinned = targets.pin_memory()
+
+    def train_step(inputs):
+        loss = model.training_step((inputs, targets_pinned, pct.clone(), tsz), 0)
+        loss.backward()
+        D.allreduce_flat_grad(flat.grad)
+        opt.step(grad_scale=1.0 / world)
+        flat.zero_grad()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    def timed(n, e2e):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lib.ds2_launch_count(1)
+        e0.record()
+        last = None
+        for _ in range(n):
+            if e2e:
+                last = float(train_step(x_pinned.to(dev, non_blocking=True)).item())   # H2D + D2H every step
+            else:
+                last = train_step(x_dev)
+        e1.record()
+        barrier()
+        launches = int(lib.ds2_launch_count(0))
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)   # max over ranks
+            ms = float(t)
+        return ms / n, launches, (last if e2e else float(last.detach()))
+
+    log(f"model built ({n_params} params), warming up")
+    for _ in range(max(3, args.warmup)):
+        train_step(x_dev)
+    torch.cuda.synchronize()
+    log("warm-up done")
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches, loss_val = timed(args.steps, e2e=False)
+    log(f"device-resident: {ms_dev:.2f} ms/step")
+    ms_e2e, _, _ = timed(args.steps, e2e=True)
+    log(f"e2e: {ms_e2e:.2f} ms/step")
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-block device times (cudaEvent ranges inside the library) for the roofline of the dominant kernel
+    prof = {}
+    if rank == 0:
+        lib.ds2_prof_enable(1)
+        for _ in range(2):
+            train_step(x_dev)
+        buf = (__import__("ctypes").c_char * 8192)()
+        lib.ds2_prof_report(buf, 8192)
+        lib.ds2_prof_enable(0)
+        for item in buf.value.decode().split(";"):
+            if item:
+                tag, ms, cnt = item.split(":")
+                prof[tag] = {"ms_per_step": float(ms) / 2, "ranges_per_step": int(cnt) // 2}
+    barrier()
+
+    if rank != 0:
+        return
+    hbm_peak, tf_peak, which = load_peaks()
+    Tp = (T - 1) // 2 + 1
+    D_ = 2 if bidir else 1
+    G = {"lstm": 4, "gru": 3, "rnn": 1}[rnn]
+    # SURVEY.md §8d algorithmic bytes of the recurrent sweep, per layer and direction:
+    #   fwd: read G_x (T'*B*G*H) + W_hh once (G*H*H) + write h (+ c for LSTM)
+    #   bwd: read dY + h,c (3*T'BH) + gates (T'B*GH) + W_hh once + write dG (T'B*GH)
+    tbh = Tp * B * H * 4
+    fwd_bytes = (G * tbh + G * H * H * 4 + tbh * (2 if rnn == "lstm" else 1)) * D_ * layers
+    bwd_bytes = ((2 * G + 3) * tbh + G * H * H * 4) * D_ * layers
+    roofs = {}
+    for tag, nbytes in (("rnn_fwd_sweep", fwd_bytes), ("rnn_bwd_sweep", bwd_bytes)):
+        if tag in prof and prof[tag]["ms_per_step"] > 0:
+            ach = nbytes / (prof[tag]["ms_per_step"] * 1e-3) / 1e9
+            roofs[tag] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                          "traffic": None, "peak_source": which, "algorithmic_bytes_per_step": nbytes,
+                          "ms_per_step": prof[tag]["ms_per_step"]}
+    dominant = max(prof, key=lambda k: prof[k]["ms_per_step"]) if prof else None
+    roofline = roofs.get(dominant) or (roofs.get("rnn_bwd_sweep") if roofs else None)
+    if roofline is not None:
+        roofline = dict(roofline, kernel=dominant if dominant in roofs else "rnn_bwd_sweep")
+
+    value = B * world / (ms_dev * 1e-3)
+    e2e = B * world / (ms_e2e * 1e-3)
+    h2d = x.numel() * 4 + targets.numel() * 8 + B * 4 * 2
+    line = {
+        "metric": "utterances/sec (train step, 161x1000 spectrogram)", "value": value, "unit": "utt/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_dev,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "rnn": f"{layers}x{'bi' if bidir else 'uni'}-{rnn}-{H}",
+                   "batch_per_gpu": B, "global_batch": B * world, "frames": T, "target_len": L, "params": n_params,
+                   "parallelism": f"dp{world}", "optimizer": "fused clip(400)+AdamW inside the step",
+                   "l2": "per-step working set (activations 3+ GB) exceeds the 126 MB L2; no explicit flush"},
+        "e2e": {"value": e2e, "unit": "utt/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches, "clocks": clocks, "loss": loss_val,
+        "roofline": roofline, "roofline_all": roofs, "blocks_ms_per_step": {k: v["ms_per_step"] for k, v in prof.items()},
+    }
+    log("profile ranges: " + json.dumps(line["blocks_ms_per_step"]))
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.workload)
+        log("cpu baseline done")
+    if args.stock_cuda:
+        try:
+            line["stock_cuda_baseline"] = stock_cuda_baseline(args.workload)
+        except Exception as e:  # pragma: no cover
+            line["stock_cuda_baseline"] = {"error": repr(e)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="librispeech", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override utterances per GPU")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--cpu-batch", type=int, default=2, help="--impl reference: utterances per CPU step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stock-cuda", action="store_true", help="also time the stock torch CUDA path (north_star denominator)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1 and int(os.environ.get("RANK", "0")) != 0:
+            try:
+                import torch
+                if torch.distributed.is_initialized():
+                    torch.distributed.destroy_process_group()
+            except Exception:
+                pass
+
+
+if __name__ == "__main__":
+    main()

@@ -1,6 +1,11 @@
 // Library-wide state: error string, launch counter, precision switch, device check, seq lens.
 #include <stdarg.h>
 
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
 #include "common.cuh"
 
 namespace ds2 {
@@ -15,6 +20,31 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 int precision() { return g_prec.load(std::memory_order_relaxed); }
+
+// ---- profiler -----------------------------------------------------------------------------------
+struct ProfRec { const char* tag; cudaEvent_t e0, e1; };
+static std::vector<ProfRec> g_recs;
+static std::vector<size_t> g_open;
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+
+void prof_begin(const char* tag, cudaStream_t st) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  r.tag = tag;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  cudaEventRecord(r.e0, st);
+  g_recs.push_back(r);
+  g_open.push_back(g_recs.size() - 1);
+}
+void prof_end(cudaStream_t st) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_open.empty()) return;
+  cudaEventRecord(g_recs[g_open.back()].e1, st);
+  g_open.pop_back();
+}
 }  // namespace ds2
 
 extern "C" {
@@ -53,6 +83,44 @@ int ds2_get_precision(void) { return ds2::precision(); }
 int64_t ds2_launch_count(int reset) {
   long long v = reset ? ds2::g_launches.exchange(0) : ds2::g_launches.load();
   return (int64_t)v;
+}
+
+int ds2_prof_enable(int on) {
+  ds2::g_prof_on.store(on ? 1 : 0);
+  return DS2_OK;
+}
+
+// Synchronises the device, then writes "tag:total_ms:count;" for every tag recorded since the last
+// call (NUL-terminated, truncated to cap) and clears the records.  Returns the number of tags.
+int ds2_prof_report(char* buf, size_t cap) {
+  using namespace ds2;
+  DS2_CHECK_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  std::map<std::string, std::pair<double, int>> agg;
+  for (auto& r : g_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      auto& a = agg[r.tag];
+      a.first += ms;
+      a.second += 1;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_recs.clear();
+  g_open.clear();
+  std::string out;
+  char tmp[160];
+  for (auto& kv : agg) {
+    snprintf(tmp, sizeof(tmp), "%s:%.4f:%d;", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += tmp;
+  }
+  if (buf && cap) {
+    size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return (int)agg.size();
 }
 
 int ds2_seq_lens_host(const int32_t* in_len, int n, int32_t* out_len) {

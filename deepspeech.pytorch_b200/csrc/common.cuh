@@ -41,6 +41,16 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
     DS2_CHECK_CUDA(cudaGetLastError());                                   \
   } while (0)
 
+// Device-time ranges (cudaEvent pairs on the launching stream), off unless ds2_prof_enable(1).
+void prof_begin(const char* tag, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfRange {
+  cudaStream_t st;
+  ProfRange(const char* tag, cudaStream_t s) : st(s) { prof_begin(tag, s); }
+  ~ProfRange() { prof_end(st); }
+};
+#define DS2_PROF(tag, st) ds2::ProfRange _prof_range_##__LINE__(tag, st)
+
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 #ifdef __CUDACC__
 __device__ __forceinline__ int cdiv_dev(int a, int b) { return (a + b - 1) / b; }

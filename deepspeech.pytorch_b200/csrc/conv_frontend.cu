@@ -462,6 +462,7 @@ int ds2_conv_frontend_fwd(int B, int T, const float* x, const int32_t* out_len, 
   const int Tp = (T - 1) / 2 + 1, D1 = DS2_CONV1_D, D2 = DS2_CONV2_D, F = DS2_NUM_FREQ;
   ConvWs W;
   conv_ws_carve(B, T, ws, &W);
+  DS2_PROF("conv_fwd", st);
   DS2_CHECK_CUDA(cudaMemsetAsync(W.sums, 0, 4 * 64 * sizeof(double), st));
   DS2_LAUNCH(pack_fwd_kernel, cdiv(41 * 11 * CO, 256), 256, 0, st, 1, 41, 11, w1, W.wpk1);
   DS2_LAUNCH(pack_fwd_kernel, cdiv(CO * 21 * 11 * CO, 256), 256, 0, st, CO, 21, 11, w2, W.wpk2);
@@ -495,6 +496,7 @@ int ds2_conv_frontend_bwd(int B, int T, const float* x, const int32_t* out_len, 
   conv_ws_carve(B, T, ws, &W);
   double* s2 = W.sums + 128;
   double* s1 = W.sums + 192;
+  DS2_PROF("conv_bwd", st);
   DS2_CHECK_CUDA(cudaMemsetAsync(s2, 0, 128 * sizeof(double), st));
   DS2_CHECK_CUDA(cudaMemsetAsync(db2, 0, CO * sizeof(float), st));
   DS2_CHECK_CUDA(cudaMemsetAsync(db1, 0, CO * sizeof(float), st));

@@ -215,6 +215,7 @@ int ds2_ctc_loss_fwd_bwd(int T, int B, int C, const float* logits, const int64_t
   if (!lp || !alpha || !beta || !offs_a || !offs_b || !loglik || !off) { set_error("ds2_ctc: arena"); return DS2_ERR_WORKSPACE; }
 
   int rows = T * B;
+  DS2_PROF("ctc", st);
   DS2_LAUNCH(ctc_logsoftmax_kernel, cdiv(rows, 8), 256, 0, st, rows, C, logits, lp);
   DS2_LAUNCH(ctc_offsets_kernel, 1, 32, 0, st, B, tgt_len, off);
   int threads = (Smax + 31) / 32 * 32;

@@ -217,6 +217,7 @@ int ds2_fc_head_fwd(int rows, int H, int C, const float* x, const float* g, cons
   DS2_REQUIRE(ws_bytes >= ds2_fc_head_workspace_bytes(rows, H, C), "ds2_fc_head_fwd: workspace too small");
   cudaStream_t st = as_stream(stream);
   Arena ar(ws, ws_bytes);
+  DS2_PROF("fc_fwd", st);
   float* xbn = ar.take<float>((size_t)rows * H);
   double* sums = ar.take<double>(2 * (size_t)H);
   int r = bn_rows_fwd(rows, H, x, g, b, rmean, rvar, training, momentum, eps, xbn, xhat, stats, sums, st);
@@ -234,6 +235,7 @@ int ds2_fc_head_bwd(int rows, int H, int C, const float* g, const float* b, cons
   DS2_REQUIRE(ws_bytes >= ds2_fc_head_workspace_bytes(rows, H, C), "ds2_fc_head_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
   Arena ar(ws, ws_bytes);
+  DS2_PROF("fc_bwd", st);
   float* tmp = ar.take<float>((size_t)rows * H);
   double* sums = ar.take<double>(2 * (size_t)H);
   void* gws = ar.base + ar.off;
@@ -270,6 +272,7 @@ int ds2_adamw_step(int64_t n, float* p, const float* g, float* m, float* v, floa
   DS2_REQUIRE(n >= 0 && step >= 1 && norm_ws, "ds2_adamw_step: bad arguments");
   cudaStream_t st = as_stream(stream);
   double* sumsq = static_cast<double*>(norm_ws);
+  DS2_PROF("optim", st);
   DS2_CHECK_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double), st));
   int blocks = (int)((n + 4095) / 4096);
   blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);

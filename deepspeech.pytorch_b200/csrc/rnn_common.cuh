@@ -1,0 +1,23 @@
+// Arguments of one recurrent sweep (all time steps of one layer, both directions).
+#pragma once
+#include <stdint.h>
+
+namespace ds2 {
+
+struct SeqArgs {
+  int T, B, H, D, G;
+  const int32_t* len;
+  float* gates;  // (T,B,D,G*H): input projections in, gate activations (fwd) / gate gradients (bwd) out
+  float* hseq;   // (D,T,B,H) per-direction outputs, zero at masked steps
+  float* aux;    // (D,T,B,H) LSTM cell states / GRU W_hn h + b_hn (-> dGh_n after bwd); null for tanh
+  const float* w_hh[2];   // fwd: (G*H,H) ; bwd: transposed (H,G*H)
+  const float* b_ih[2];
+  const float* b_hh[2];
+  const float* h0;        // (D,B,H) or null
+  const float* c0;
+  const float* dy;        // bwd: (T,B,H)
+  float* carry;           // bwd: (D,B,H) dc (LSTM) / dh (GRU)
+  int training;
+};
+
+}  // namespace ds2

@@ -11,27 +11,12 @@
 //                           GRU W_hn h + b_hn; absent for tanh) | bn mean,invstd (2*In)
 #include "common.cuh"
 #include "rnn_cells.cuh"
+#include "rnn_common.cuh"
 
 namespace ds2 {
 
 constexpr int UT = 8;   // hidden units per CTA
 constexpr int KC = 64;  // reduction chunk staged in shared memory
-
-struct SeqArgs {
-  int T, B, H, D, G;
-  const int32_t* len;
-  float* gates;  // (T,B,D,G*H)
-  float* hseq;   // (D,T,B,H)
-  float* aux;    // (D,T,B,H) or null
-  const float* w_hh[2];   // fwd: (G*H,H) ; bwd: transposed (H,G*H)
-  const float* b_ih[2];
-  const float* b_hh[2];
-  const float* h0;        // (D,B,H) or null
-  const float* c0;
-  const float* dy;        // bwd: (T,B,H)
-  float* carry;           // bwd: (D,B,H) dc (LSTM) / dh (GRU)
-  int training;
-};
 
 __device__ __forceinline__ int gates_per(int rnn) { return rnn == DS2_RNN_LSTM ? 4 : (rnn == DS2_RNN_GRU ? 3 : 1); }
 
@@ -338,20 +323,26 @@ int ds2_rnn_layer_fwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
   void* gws = ar.base + ar.off;
   size_t gws_bytes = ar.cap - ar.off;
   // input projection for every time step and both directions: gates[:, d*GH:(d+1)*GH] = xin . W_ih[d]^T
-  for (int dir = 0; dir < D; ++dir) {
-    rc = ds2_gemm(0, 1, TB, GH, In, 1.f, xin, In, w_ih[dir], In, 0.f, R.gates + (size_t)dir * GH, D * GH, gws,
-                  gws_bytes, stream);
-    if (rc) return rc;
+  {
+    DS2_PROF("rnn_fwd_proj_gemm", st);
+    for (int dir = 0; dir < D; ++dir) {
+      rc = ds2_gemm(0, 1, TB, GH, In, 1.f, xin, In, w_ih[dir], In, 0.f, R.gates + (size_t)dir * GH, D * GH, gws,
+                    gws_bytes, stream);
+      if (rc) return rc;
+    }
   }
   SeqArgs a{};
   a.T = T; a.B = B; a.H = H; a.D = D; a.G = G; a.len = len;
   a.gates = R.gates; a.hseq = R.hseq; a.aux = R.aux;
   for (int dir = 0; dir < D; ++dir) { a.w_hh[dir] = w_hh[dir]; a.b_ih[dir] = b_ih[dir]; a.b_hh[dir] = b_hh[dir]; }
   a.h0 = h0; a.c0 = c0; a.training = d->training;
-  rc = 1;
-  if (precision() == DS2_PREC_TF32) rc = rnn_sweep_fwd_tc(d->rnn_type, a, gws, gws_bytes, st);
-  if (rc == 1) rc = sweep_fwd(d->rnn_type, a, st);
-  if (rc) return rc;
+  {
+    DS2_PROF("rnn_fwd_sweep", st);
+    rc = 1;
+    if (precision() == DS2_PREC_TF32) rc = rnn_sweep_fwd_tc(d->rnn_type, a, gws, gws_bytes, st);
+    if (rc == 1) rc = sweep_fwd(d->rnn_type, a, st);
+    if (rc) return rc;
+  }
   size_t n = (size_t)TB * H;
   int blocks = (int)((n + 1023) / 1024);
   blocks = blocks > 148 * 16 ? 148 * 16 : blocks;
@@ -399,10 +390,13 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
   a.gates = R.gates; a.hseq = R.hseq; a.aux = R.aux;
   for (int dir = 0; dir < D; ++dir) { a.w_hh[dir] = wT[dir]; a.b_ih[dir] = b_ih[dir]; a.b_hh[dir] = b_hh[dir]; }
   a.dy = dy; a.carry = carry; a.training = 1;
-  rc = 1;
-  if (precision() == DS2_PREC_TF32) rc = rnn_sweep_bwd_tc(d->rnn_type, a, gws, gws_bytes, st);
-  if (rc == 1) rc = sweep_bwd(d->rnn_type, a, st);
-  if (rc) return rc;
+  {
+    DS2_PROF("rnn_bwd_sweep", st);
+    rc = 1;
+    if (precision() == DS2_PREC_TF32) rc = rnn_sweep_bwd_tc(d->rnn_type, a, gws, gws_bytes, st);
+    if (rc == 1) rc = sweep_bwd(d->rnn_type, a, st);
+    if (rc) return rc;
+  }
 
   // the layer input as the projection saw it (BN applied) and its normalised form for the BN backward
   const float* xin = x;
@@ -413,6 +407,7 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
     xin = xbn;
   }
   const bool gru = d->rnn_type == DS2_RNN_GRU;
+  DS2_PROF("rnn_bwd_gemms", st);
   for (int dir = 0; dir < D; ++dir) {
     const float* dG = R.gates + (size_t)dir * GH;   // (TB, GH) with row stride D*GH : dGx
     const int ldg = D * GH;

@@ -1,8 +1,599 @@
-// placeholder until the tcgen05 persistent sweep lands
+// Persistent, warp-specialised recurrent sweeps on tcgen05.
+//
+// One launch per layer covers ALL time steps and both directions.  A CTA owns 16 hidden units of
+// one direction: the G*16 rows of W_hh for those units form the M=64 operand of
+//     acc[(g,u), b] = sum_k W_hh[g*H+u, k] * h_{t-1}[b, k]        (tcgen05.mma kind::tf32, N = batch)
+// with fp32 accumulators in TMEM.  Per step:
+//   warp 0   TMA producer: weight chunks (3-D box over [gate][unit][k], prefetched ahead of the
+//            barrier because they do not depend on it) and h_{t-1} chunks (after the grid barrier)
+//            into an 8-stage 128B-swizzled shared-memory ring
+//   warp 1   single-thread MMA issue, tcgen05.commit -> mbarriers
+//   warps 2-5 epilogue: TMEM -> registers, + input projection + biases, gate non-linearities spread
+//            over 64 lanes, exchange through shared memory, cell update (c / h state stays in shared
+//            memory for the whole sweep), masked stores of h_t (and the saved tensors for backward)
+// Steps are separated by a per-direction grid barrier (monotonic counter in global memory, release /
+// acquire, bounded spin so that a fault cannot hang the GPU).  All CTAs must be co-resident: the host
+// checks occupancy and launches cooperatively; shapes that do not fit return 1 (FFMA step kernels).
+//
+// Backward sweep: the same skeleton on W_hh^T with split-K over the gates inside a 4-CTA cluster
+// (partial sums reduced through distributed shared memory) — see rnn_bwd_persist_kernel.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "rnn_cells.cuh"
+#include "rnn_common.cuh"
+#include "tc_common.cuh"
+
+namespace cg = cooperative_groups;
+
 namespace ds2 {
-struct SeqArgs;
-int rnn_sweep_fwd_tc(int, const SeqArgs&, void*, size_t, cudaStream_t) { return 1; }
-int rnn_sweep_bwd_tc(int, const SeqArgs&, void*, size_t, cudaStream_t) { return 1; }
-size_t rnn_sweep_tc_workspace_bytes(int, int, int, int, int) { return 0; }
+
+namespace rp {
+constexpr int UT = 16;        // hidden units per CTA
+constexpr int MM = 64;        // MMA M (G*UT rows, padded for GRU / tanh)
+constexpr int BK = 32;        // fp32 elements per 128-byte swizzle row
+constexpr int STAGES = 8;
+constexpr int THREADS = 192;  // producer, mma, 4 epilogue warps
+constexpr int A_BYTES = MM * 128;
+constexpr long long SPIN_LIMIT = 4000000000LL;   // ~2 s of SM clocks
+}  // namespace rp
+
+struct PersistParams {
+  CUtensorMap tmW[2];   // 3-D (k, unit, gate) over W_hh[d]
+  CUtensorMap tmV[2];   // 2-D (k, row) over the per-direction vector sequence (hseq[d] as [T*B, H])
+  CUtensorMap tmV2[2];  // bwd GRU: the n-gate part of dGh lives in the aux buffer
+  int T, B, NB, H, D, NT, G, training;
+  const float* dy;      // bwd: (T,B,H)
+  long long* trace;     // optional: clock64 stamps of CTA 0, 4 per step
+  const int32_t* len;
+  float* gates;
+  float* hseq;
+  float* aux;
+  const float* b_ih[2];
+  const float* b_hh[2];
+  unsigned int* bar;    // [2] per-direction arrival counters (zeroed by the host)
+  int* err;             // set to 1 if a barrier wait timed out
+};
+
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
+__device__ __forceinline__ void red_release(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// wait until *bar >= target (bounded)
+__device__ __forceinline__ void grid_wait(const unsigned int* bar, unsigned int target, int* err) {
+  if (ld_acquire(bar) >= target) return;
+  const long long t0 = clock64();
+  while (ld_acquire(bar) < target) {
+    if (*(volatile int*)err) return;
+    if (clock64() - t0 > rp::SPIN_LIMIT) {
+      *(volatile int*)err = 1;
+      printf("ds2: recurrent sweep barrier timeout (block %d, target %u, have %u)\n", blockIdx.x, target,
+             ld_acquire(bar));
+      return;
+    }
+  }
+}
+
+__device__ __forceinline__ void trace_stamp(long long* trace, int step, int slot) {
+  if (trace && blockIdx.x == 0) trace[(size_t)step * 6 + slot] = clock64();
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int RNN>
+__global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const __grid_constant__ PersistParams p) {
+  using namespace rp;
+  using namespace tc;
+  constexpr int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int NB = p.NB, B = p.B, T = p.T, H = p.H, D = p.D;
+  const int B_BYTES = NB * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  const int NBp = NB + 1;
+  float* ex = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);   // [4][UT][NBp]
+  float* cst = ex + 4 * UT * NBp;                                       // [UT][NBp] cell (LSTM) / hidden (GRU) state
+  uint64_t* full = reinterpret_cast<uint64_t*>(cst + UT * NBp + ((UT * NBp) & 1));
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum_bar = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int d = blockIdx.x / p.NT, tile = blockIdx.x % p.NT, u0 = tile * UT;
+  const int NK = H / BK;
+  const int GH = G * H;
+  unsigned int* bar = p.bar + d;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmW[d]);
+    tma_prefetch_desc(&p.tmV[d]);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < UT * NBp; i += THREADS) cst[i] = 0.f;
+  if (warp == 1) {
+    // TMEM columns: power of two >= max(32, NB)
+    if (NB <= 32) tmem_alloc<32>(tmem_slot);
+    else if (NB <= 64) tmem_alloc<64>(tmem_slot);
+    else if (NB <= 128) tmem_alloc<128>(tmem_slot);
+    else tmem_alloc<256>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tx_bytes = (uint32_t)(G * UT * 128 + B * 128);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // two cursors over the chunk sequence (steps 1..T-1, NK chunks each): weights run ahead of the barrier
+      const long long total = (long long)(T - 1) * NK;
+      long long wc = 0, ac = 0;
+      while (ac < total) {
+        while (wc < total && wc - ac < STAGES) {
+          const int s = (int)(wc % STAGES);
+          const uint32_t ph = (uint32_t)((wc / STAGES) & 1);
+          if (!mbar_try_wait(&empty[s], ph ^ 1)) break;
+          mbar_arrive_expect_tx(&full[s], tx_bytes);
+          tma_load_3d(smem + s * STAGE_BYTES, &p.tmW[d], &full[s], (int)(wc % NK) * BK, u0, 0);
+          ++wc;
+        }
+        if (wc > ac) {
+          const int step = 1 + (int)(ac / NK), c = (int)(ac % NK);
+          const int t = d == 0 ? step : T - 1 - step;
+          const int tp = d == 0 ? t - 1 : t + 1;
+          if (c == 0) {
+            grid_wait(bar, (unsigned int)p.NT * (unsigned int)step, p.err);
+            fence_proxy_async_all();
+            trace_stamp(p.trace, step, 0);
+          }
+          const int s = (int)(ac % STAGES);
+          tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &p.tmV[d], &full[s], c * BK, tp * B);
+          ++ac;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(FMT_TF32, MM, NB);
+      long long ch = 0;
+      for (int step = 1; step < T; ++step) {
+        for (int c = 0; c < NK; ++c, ++ch) {
+          const int s = (int)(ch % STAGES);
+          const uint32_t ph = (uint32_t)((ch / STAGES) & 1);
+          mbar_wait(&full[s], ph);
+          if (c == 0) trace_stamp(p.trace, step, 1);
+          if (c == NK - 1) trace_stamp(p.trace, step, 2);
+          tc_fence_after();
+          const uint64_t adesc = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES));
+          const uint64_t bdesc = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k)
+            mma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (c | k) != 0);
+          mma_commit(&empty[s]);
+        }
+        mma_commit(accum_bar);
+      }
+    }
+  } else {
+    // ---------------- epilogue warps: quarter q of TMEM == gate q (rows q*16 .. q*16+15 in lanes 0..15)
+    const int q = warp % 4;
+    const int e = threadIdx.x - 64;          // 0..127
+    const bool act_lane = lane < UT;
+    const int u = u0 + lane;                 // valid when act_lane
+    float bias_x = 0.f, bias_h = 0.f;        // b_ih / b_hh of this thread's (gate q, unit u)
+    if (act_lane && q < G) { bias_x = p.b_ih[d][q * H + u]; bias_h = p.b_hh[d][q * H + u]; }
+    float bias_xn = 0.f;                     // GRU: warp 3 carries x_n + b_in
+    if (RNN == DS2_RNN_GRU && act_lane && q == 3) bias_xn = p.b_ih[d][2 * H + u];
+    uint32_t acc_phase = 0;
+    for (int step = 0; step < T; ++step) {
+      const int t = d == 0 ? step : T - 1 - step;
+      // input-projection values of this thread for every batch column (independent of the recurrence)
+      for (int cb = 0; cb < NB; cb += 32) {
+        float gx[32];
+        const int gsel = (RNN == DS2_RNN_GRU && q == 3) ? 2 : q;
+        const bool need_gx = act_lane && (q < G || (RNN == DS2_RNN_GRU && q == 3));
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int b = cb + j;
+          gx[j] = (need_gx && b < B) ? p.gates[(((size_t)t * B + b) * D + d) * GH + (size_t)gsel * H + u] : 0.f;
+        }
+        float acc[32];
+        if (step > 0 && q < G) {
+          if (cb == 0) { mbar_wait(accum_bar, acc_phase); tc_fence_after(); if (e == 0) trace_stamp(p.trace, step, 3); }
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, acc);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+        }
+        if (act_lane) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int b = cb + j;
+            if (b >= B) break;
+            float v;
+            if (RNN == DS2_RNN_LSTM) {
+              float pre = gx[j] + bias_x + acc[j] + bias_h;
+              v = (q == 2) ? tanhf(pre) : sigmoidf_(pre);
+            } else if (RNN == DS2_RNN_GRU) {
+              if (q < 2) v = sigmoidf_(gx[j] + bias_x + acc[j] + bias_h);
+              else if (q == 2) v = acc[j] + bias_h;          // W_hn h + b_hn
+              else v = gx[j] + bias_xn;                      // x_n + b_in
+            } else {
+              v = (q == 0) ? tanhf(gx[j] + bias_x + acc[j] + bias_h) : 0.f;
+            }
+            ex[(q * UT + lane) * NBp + b] = v;
+          }
+        }
+      }
+      if (step > 0) acc_phase ^= 1;
+      tc_fence_before();
+      named_bar_sync(1, 128);
+      if (e == 0) trace_stamp(p.trace, step, 4);
+      // ---------------- combine: (unit, batch) pairs over the 128 epilogue threads
+      for (int pi = e; pi < UT * B; pi += 128) {
+        const int ui = pi % UT, b = pi / UT;
+        const bool valid = t < p.len[b];
+        const size_t so = (((size_t)d * T + t) * B + b) * H + u0 + ui;
+        float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + ui;
+        const float e0 = ex[(0 * UT + ui) * NBp + b], e1 = ex[(1 * UT + ui) * NBp + b];
+        const float e2 = ex[(2 * UT + ui) * NBp + b], e3 = ex[(3 * UT + ui) * NBp + b];
+        float hval = 0.f;
+        if (RNN == DS2_RNN_LSTM) {
+          float cval = 0.f;
+          if (valid) {
+            cval = fmaf(e1, cst[ui * NBp + b], e0 * e2);
+            hval = e3 * tanhf(cval);
+            cst[ui * NBp + b] = cval;
+          }
+          p.aux[so] = cval;
+          if (p.training) {
+            gp[0] = valid ? e0 : 0.f; gp[H] = valid ? e1 : 0.f; gp[2 * H] = valid ? e2 : 0.f;
+            gp[3 * H] = valid ? e3 : 0.f;
+          }
+        } else if (RNN == DS2_RNN_GRU) {
+          float nval = 0.f;
+          if (valid) {
+            const float hprev = cst[ui * NBp + b];
+            nval = tanhf(fmaf(e0, e2, e3));
+            hval = fmaf(e1, hprev - nval, nval);
+            cst[ui * NBp + b] = hval;
+          }
+          p.aux[so] = valid ? e2 : 0.f;
+          if (p.training) { gp[0] = valid ? e0 : 0.f; gp[H] = valid ? e1 : 0.f; gp[2 * H] = nval; }
+        } else {
+          hval = valid ? e0 : 0.f;
+          if (p.training) gp[0] = hval;
+        }
+        p.hseq[so] = hval;
+      }
+      __threadfence();
+      fence_proxy_async_all();
+      named_bar_sync(1, 128);
+      if (e == 0) { red_release(bar, 1u); trace_stamp(p.trace, step, 5); }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    if (NB <= 32) tmem_dealloc<32>(tmem_base);
+    else if (NB <= 64) tmem_dealloc<64>(tmem_base);
+    else if (NB <= 128) tmem_dealloc<128>(tmem_base);
+    else tmem_dealloc<256>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+static long long* trace_ptr_from_env(const char* name) {
+  const char* e = getenv(name);   // debug: device address of an int64 buffer of 6*T entries
+  return e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 10)) : nullptr;
+}
+
+static size_t fwd_smem_bytes(int NB) {
+  using namespace rp;
+  size_t NBp = NB + 1;
+  return 1024 + (size_t)STAGES * (A_BYTES + (size_t)NB * 128) + (5 * UT * NBp + 2) * sizeof(float) +
+         (2 * STAGES + 2) * sizeof(uint64_t) + 64;
+}
+
+size_t rnn_sweep_tc_workspace_bytes(int, int, int, int, int) { return 1024; }
+
+static bool fwd_eligible(const SeqArgs& a) {
+  if (a.h0 || a.c0) return false;                 // initial states -> generic step kernels
+  if (a.H % 32 != 0 || a.B > 256 || a.T < 2) return false;
+  return true;
+}
+
+template <int RNN>
+static int launch_fwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
+  using namespace rp;
+  const int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
+  PersistParams p{};
+  p.T = a.T; p.B = a.B; p.NB = (a.B + 7) / 8 * 8; p.H = a.H; p.D = a.D; p.NT = a.H / UT; p.G = G;
+  p.training = a.training;
+  p.len = a.len; p.gates = a.gates; p.hseq = a.hseq; p.aux = a.aux;
+  p.trace = trace_ptr_from_env("DS2_TRACE_FWD");
+  if (ws_bytes < 1024) return 1;
+  p.bar = static_cast<unsigned int*>(ws);
+  p.err = reinterpret_cast<int*>(static_cast<char*>(ws) + 64);
+  const size_t smem = fwd_smem_bytes(p.NB);
+  auto kern = rnn_fwd_persist_kernel<RNN>;
+  static bool attr_done = false;
+  static int max_blocks_per_sm = 0, num_sms = 0;
+  if (!attr_done) {
+    DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int dev = 0;
+    DS2_CHECK_CUDA(cudaGetDevice(&dev));
+    DS2_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_done = true;
+  }
+  if (smem > 227 * 1024) return 1;
+  DS2_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, kern, THREADS, smem));
+  const int grid = a.D * p.NT;
+  if (max_blocks_per_sm < 1 || grid > max_blocks_per_sm * num_sms) return 1;   // cannot be co-resident
+  for (int d = 0; d < a.D; ++d) {
+    p.b_ih[d] = a.b_ih[d];
+    p.b_hh[d] = a.b_hh[d];
+    int rc = make_tmap_3d(&p.tmW[d], a.w_hh[d], a.H, a.H, G, (size_t)a.H, (size_t)a.H * a.H, BK, UT, G);
+    if (rc) return rc;
+    rc = make_tmap_2d(&p.tmV[d], a.hseq + (size_t)d * a.T * a.B * a.H, a.T * a.B, a.H, a.H, a.B, BK);
+    if (rc) return rc;
+  }
+  DS2_CHECK_CUDA(cudaMemsetAsync(ws, 0, 128, st));
+  void* args[] = {&p};
+  DS2_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(THREADS), args, smem, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return DS2_OK;
+}
+
+int rnn_sweep_fwd_tc(int rnn, const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!fwd_eligible(a)) return 1;
+  if (rnn == DS2_RNN_LSTM) return launch_fwd<DS2_RNN_LSTM>(a, ws, ws_bytes, st);
+  if (rnn == DS2_RNN_GRU) return launch_fwd<DS2_RNN_GRU>(a, ws, ws_bytes, st);
+  return launch_fwd<DS2_RNN_TANH>(a, ws, ws_bytes, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward sweep.  A CTA owns 16 hidden units of one direction: rows u0..u0+15 of W_hh^T (H x G*H)
+// are the (16 valid of 64) M rows, the gate-gradient vector of the previously processed step
+// dGh[t_next] (B x G*H) is the N operand, K = G*H:
+//     dh_rec[u, b] = sum_k W_hh^T[u, k] * dGh[t_next][b, k]
+// Epilogue: dh = dY[t] + dh_rec (+ carried terms), gate backward from the saved activations, the
+// gate gradients overwrite the activations in place (and are the next step's N operand).  The
+// cell-state / hidden-state carry of the owned units stays in shared memory for the whole sweep.
+template <int RNN>
+__global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const __grid_constant__ PersistParams p) {
+  using namespace rp;
+  using namespace tc;
+  constexpr int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int NB = p.NB, B = p.B, T = p.T, H = p.H, D = p.D;
+  const int B_BYTES = NB * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  const int NBp = NB + 1;
+  float* ex = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);   // [UT][NBp] dh_rec
+  float* cst = ex + 4 * UT * NBp;                                       // [UT][NBp] carried dc (LSTM) / dh (GRU)
+  uint64_t* full = reinterpret_cast<uint64_t*>(cst + UT * NBp);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum_bar = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int d = blockIdx.x / p.NT, tile = blockIdx.x % p.NT, u0 = tile * UT;
+  const int GH = G * H;
+  const int NK = GH / BK;
+  unsigned int* bar = p.bar + d;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmW[d]);
+    tma_prefetch_desc(&p.tmV[d]);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < UT * NBp; i += THREADS) { cst[i] = 0.f; ex[i] = 0.f; }
+  if (warp == 1) {
+    if (NB <= 32) tmem_alloc<32>(tmem_slot);
+    else if (NB <= 64) tmem_alloc<64>(tmem_slot);
+    else if (NB <= 128) tmem_alloc<128>(tmem_slot);
+    else tmem_alloc<256>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tx_bytes = (uint32_t)(UT * 128 + B * 128);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const long long total = (long long)(T - 1) * NK;
+      long long wc = 0, ac = 0;
+      while (ac < total) {
+        while (wc < total && wc - ac < STAGES) {
+          const int s = (int)(wc % STAGES);
+          const uint32_t ph = (uint32_t)((wc / STAGES) & 1);
+          if (!mbar_try_wait(&empty[s], ph ^ 1)) break;
+          mbar_arrive_expect_tx(&full[s], tx_bytes);
+          tma_load_2d(smem + s * STAGE_BYTES, &p.tmW[d], &full[s], (int)(wc % NK) * BK, u0);
+          ++wc;
+        }
+        if (wc > ac) {
+          const int step = 1 + (int)(ac / NK), c = (int)(ac % NK);
+          const int t = d == 0 ? T - 1 - step : step;
+          const int tn = d == 0 ? t + 1 : t - 1;
+          if (c == 0) {
+            grid_wait(bar, (unsigned int)p.NT * (unsigned int)step, p.err);
+            fence_proxy_async_all();
+            trace_stamp(p.trace, step, 0);
+          }
+          const int s = (int)(ac % STAGES);
+          const int k0 = c * BK;
+          if (RNN == DS2_RNN_GRU && k0 >= 2 * H)
+            tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &p.tmV2[d], &full[s], k0 - 2 * H, tn * B);
+          else
+            tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &p.tmV[d], &full[s], d * GH + k0, tn * B);
+          ++ac;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(FMT_TF32, MM, NB);
+      long long ch = 0;
+      for (int step = 1; step < T; ++step) {
+        for (int c = 0; c < NK; ++c, ++ch) {
+          const int s = (int)(ch % STAGES);
+          const uint32_t ph = (uint32_t)((ch / STAGES) & 1);
+          mbar_wait(&full[s], ph);
+          if (c == 0) trace_stamp(p.trace, step, 1);
+          if (c == NK - 1) trace_stamp(p.trace, step, 2);
+          tc_fence_after();
+          const uint64_t adesc = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES));
+          const uint64_t bdesc = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k)
+            mma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (c | k) != 0);
+          mma_commit(&empty[s]);
+        }
+        mma_commit(accum_bar);
+      }
+    }
+  } else {
+    const int q = warp % 4;
+    const int e = threadIdx.x - 64;
+    uint32_t acc_phase = 0;
+    for (int step = 0; step < T; ++step) {
+      const int t = d == 0 ? T - 1 - step : step;
+      const int tp = d == 0 ? t - 1 : t + 1;
+      const bool tp_in = tp >= 0 && tp < T;
+      if (q == 0 && step > 0) {          // rows 0..15 of the accumulator live in lanes 0..15 of quarter 0
+        mbar_wait(accum_bar, acc_phase);
+        tc_fence_after();
+        if (lane == 0) trace_stamp(p.trace, step, 3);
+        for (int cb = 0; cb < NB; cb += 32) {
+          float acc[32];
+          tmem_ld32(tmem_base + (uint32_t)cb, acc);
+          if (lane < UT) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (cb + j < B) ex[lane * NBp + cb + j] = acc[j];
+          }
+        }
+      }
+      if (step > 0) acc_phase ^= 1;
+      tc_fence_before();
+      named_bar_sync(1, 128);
+      if (e == 0) trace_stamp(p.trace, step, 4);
+      for (int pi = e; pi < UT * B; pi += 128) {
+        const int ui = pi % UT, b = pi / UT;
+        const bool valid = t < p.len[b];
+        const bool pin = tp_in && (d == 0 || tp < p.len[b]);
+        const size_t si = (((size_t)d * T + t) * B + b) * H + u0 + ui;
+        const size_t sp = (((size_t)d * T + (tp_in ? tp : 0)) * B + b) * H + u0 + ui;
+        float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + ui;
+        if (!valid) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) gp[g * H] = 0.f;
+          if (RNN == DS2_RNN_GRU) p.aux[si] = 0.f;
+        } else {
+          float dh = p.dy[((size_t)t * B + b) * H + u0 + ui] + ex[ui * NBp + b];
+          if (RNN == DS2_RNN_LSTM) {
+            const float c_prev = pin ? p.aux[sp] : 0.f;
+            LstmBwd r = lstm_cell_bwd(gp[0], gp[H], gp[2 * H], gp[3 * H], p.aux[si], c_prev, dh, cst[ui * NBp + b]);
+            gp[0] = r.di; gp[H] = r.df; gp[2 * H] = r.dg; gp[3 * H] = r.d_o;
+            cst[ui * NBp + b] = r.dc_prev;
+          } else if (RNN == DS2_RNN_GRU) {
+            const float h_prev = pin ? p.hseq[sp] : 0.f;
+            dh += cst[ui * NBp + b];
+            GruBwd r = gru_cell_bwd(gp[0], gp[H], gp[2 * H], p.aux[si], h_prev, dh);
+            gp[0] = r.dr; gp[H] = r.dz; gp[2 * H] = r.dxn;
+            p.aux[si] = r.dhn;
+            cst[ui * NBp + b] = r.dh_prev;
+          } else {
+            const float h = p.hseq[si];
+            gp[0] = dh * (1.f - h * h);
+          }
+        }
+      }
+      __threadfence();
+      fence_proxy_async_all();
+      named_bar_sync(1, 128);
+      if (e == 0) { red_release(bar, 1u); trace_stamp(p.trace, step, 5); }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    if (NB <= 32) tmem_dealloc<32>(tmem_base);
+    else if (NB <= 64) tmem_dealloc<64>(tmem_base);
+    else if (NB <= 128) tmem_dealloc<128>(tmem_base);
+    else tmem_dealloc<256>(tmem_base);
+  }
+}
+
+template <int RNN>
+static int launch_bwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
+  using namespace rp;
+  const int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
+  const int GH = G * a.H;
+  PersistParams p{};
+  p.T = a.T; p.B = a.B; p.NB = (a.B + 7) / 8 * 8; p.H = a.H; p.D = a.D; p.NT = a.H / UT; p.G = G;
+  p.training = 1;
+  p.len = a.len; p.gates = a.gates; p.hseq = a.hseq; p.aux = a.aux; p.dy = a.dy;
+  p.trace = trace_ptr_from_env("DS2_TRACE_BWD");
+  if (ws_bytes < 1024) return 1;
+  p.bar = static_cast<unsigned int*>(ws);
+  p.err = reinterpret_cast<int*>(static_cast<char*>(ws) + 64);
+  const size_t smem = fwd_smem_bytes(p.NB);
+  auto kern = rnn_bwd_persist_kernel<RNN>;
+  static bool attr_done = false;
+  static int num_sms = 0;
+  if (!attr_done) {
+    DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int dev = 0;
+    DS2_CHECK_CUDA(cudaGetDevice(&dev));
+    DS2_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_done = true;
+  }
+  if (smem > 227 * 1024) return 1;
+  int max_blocks_per_sm = 0;
+  DS2_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, kern, THREADS, smem));
+  const int grid = a.D * p.NT;
+  if (max_blocks_per_sm < 1 || grid > max_blocks_per_sm * num_sms) return 1;
+  for (int d = 0; d < a.D; ++d) {
+    // a.w_hh[d] is the transposed recurrent matrix (H, G*H) here
+    int rc = make_tmap_2d(&p.tmW[d], a.w_hh[d], a.H, GH, GH, UT, BK);
+    if (rc) return rc;
+    // gate gradients: rows (t,b), full row width D*GH (the direction offset is a coordinate)
+    rc = make_tmap_2d(&p.tmV[d], a.gates, a.T * a.B, a.D * GH, a.D * GH, a.B, BK);
+    if (rc) return rc;
+    if (RNN == DS2_RNN_GRU) {
+      rc = make_tmap_2d(&p.tmV2[d], a.aux + (size_t)d * a.T * a.B * a.H, a.T * a.B, a.H, a.H, a.B, BK);
+      if (rc) return rc;
+    }
+  }
+  DS2_CHECK_CUDA(cudaMemsetAsync(ws, 0, 128, st));
+  void* args[] = {&p};
+  DS2_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(THREADS), args, smem, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return DS2_OK;
+}
+
+int rnn_sweep_bwd_tc(int rnn, const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (a.H % 32 != 0 || a.B > 256 || a.T < 2) return 1;
+  if (rnn == DS2_RNN_LSTM) return launch_bwd<DS2_RNN_LSTM>(a, ws, ws_bytes, st);
+  if (rnn == DS2_RNN_GRU) return launch_bwd<DS2_RNN_GRU>(a, ws, ws_bytes, st);
+  return launch_bwd<DS2_RNN_TANH>(a, ws, ws_bytes, st);
+}
+
+
+}  // namespace ds2

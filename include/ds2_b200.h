@@ -58,6 +58,11 @@ int ds2_get_precision(void);
 /* Kernel-launch counter (all kernels launched by this library since the last reset). */
 int64_t ds2_launch_count(int reset);
 
+/* Device-time ranges around the kernel groups of each block (cudaEvent pairs on the launching stream).
+ * ds2_prof_report synchronises, writes "tag:total_ms:count;..." into buf and clears the records.     */
+int ds2_prof_enable(int on);
+int ds2_prof_report(char* buf, size_t cap);
+
 /* ---- lengths: DeepSpeech.get_seq_lens, model.py:299-310 (host integers, bit-exact) ---------- */
 int ds2_seq_lens_host(const int32_t* in_len_host, int n, int32_t* out_len_host);
 

@@ -1,0 +1,55 @@
+"""world_size-2 gloo test of the data-parallel exchange (host-side logic, CPU)."""
+import os
+import socket
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from deepspeech_pytorch_b200 import dist as D
+    r, w, _ = D.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    g = torch.Generator().manual_seed(100 + rank)
+    grad = torch.randn(1000, generator=g)
+    local = grad.clone()
+    D.allreduce_flat_grad(grad)
+    # mean over ranks == DDP semantics once grad_scale = 1/world is applied
+    ref = sum(torch.randn(1000, generator=torch.Generator().manual_seed(100 + k)) for k in range(world))
+    assert torch.allclose(grad, ref, atol=1e-6)
+    assert not torch.equal(grad, local)
+    m = torch.nn.BatchNorm1d(4)
+    m.running_mean.fill_(float(rank + 1))
+    D.broadcast_buffers(m, src=0)
+    assert float(m.running_mean[0]) == 1.0
+    assert D.shard_bins(7, rank, world) == list(range(7))[rank::world]
+    dist.destroy_process_group()
+    out.put(rank)
+
+
+def test_flat_gradient_allreduce_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(q.get() for _ in range(2)) == [0, 1]
