@@ -52,7 +52,8 @@ struct PersistParams {
   float* aux;
   const float* b_ih[2];
   const float* b_hh[2];
-  unsigned int* bar;    // [2] per-direction arrival counters (zeroed by the host)
+  unsigned int* bar;    // [2][NT] per-CTA step flags (zeroed by the host): flag = number of finished steps
+  int nacc, acc_cols;   // independent TMEM accumulator chains (K is dealt round-robin over them)
   int* err;             // set to 1 if a barrier wait timed out
 };
 
@@ -66,20 +67,60 @@ __device__ __forceinline__ void red_release(unsigned int* p, unsigned int v) {
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// wait until *bar >= target (bounded)
-__device__ __forceinline__ void grid_wait(const unsigned int* bar, unsigned int target, int* err) {
-  if (ld_acquire(bar) >= target) return;
+// Grid barrier of one direction: every CTA publishes the number of steps it has finished in its own
+// 4-byte flag (plain release store, no atomic serialisation); a whole warp polls all NT flags
+// (coalesced acquire loads) until each is >= target.  Bounded spin: a fault cannot hang the GPU.
+__device__ __forceinline__ unsigned int ld_relaxed(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_wait_flags(const unsigned int* flags, int nt, unsigned int target, int* err) {
+  const int lane = threadIdx.x % 32;
   const long long t0 = clock64();
-  while (ld_acquire(bar) < target) {
-    if (*(volatile int*)err) return;
-    if (clock64() - t0 > rp::SPIN_LIMIT) {
-      *(volatile int*)err = 1;
-      printf("ds2: recurrent sweep barrier timeout (block %d, target %u, have %u)\n", blockIdx.x, target,
-             ld_acquire(bar));
-      return;
+  unsigned int it = 0;
+  for (;;) {
+    // up to 4 independent loads in flight per lane (nt <= 128 flags per direction), relaxed polling
+    unsigned int v0 = lane < nt ? ld_relaxed(flags + lane) : target;
+    unsigned int v1 = lane + 32 < nt ? ld_relaxed(flags + lane + 32) : target;
+    unsigned int v2 = lane + 64 < nt ? ld_relaxed(flags + lane + 64) : target;
+    unsigned int v3 = lane + 96 < nt ? ld_relaxed(flags + lane + 96) : target;
+    bool ok = v0 >= target && v1 >= target && v2 >= target && v3 >= target;
+    for (int i = lane + 128; i < nt; i += 32) ok = ok && (ld_relaxed(flags + i) >= target);
+    if (__all_sync(0xffffffffu, ok)) break;
+    if ((++it & 63u) == 0) {
+      if (*(volatile int*)err) return;
+      if (clock64() - t0 > rp::SPIN_LIMIT) {
+        *(volatile int*)err = 1;
+        if (lane == 0) printf("ds2: recurrent sweep barrier timeout (block %d, target %u)\n", blockIdx.x, target);
+        return;
+      }
+    }
+  }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire side of the flag protocol
+}
+// single-thread variant on a monotonically increasing arrival counter
+__device__ __forceinline__ void grid_wait_counter(const unsigned int* ctr, unsigned int target, int* err) {
+  if (ld_acquire(ctr) >= target) return;
+  const long long t0 = clock64();
+  unsigned int it = 0;
+  while (ld_acquire(ctr) < target) {
+    if ((++it & 255u) == 0) {
+      if (*(volatile int*)err) return;
+      if (clock64() - t0 > rp::SPIN_LIMIT) {
+        *(volatile int*)err = 1;
+        printf("ds2: recurrent sweep barrier timeout (block %d, target %u, have %u)\n", blockIdx.x, target,
+               ld_acquire(ctr));
+        return;
+      }
     }
   }
 }
+__device__ __forceinline__ void st_release(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.f, fast_sigmoid(2.f * x), -1.f); }
 
 __device__ __forceinline__ void trace_stamp(long long* trace, int step, int slot) {
   if (trace && blockIdx.x == 0) trace[(size_t)step * 6 + slot] = clock64();
@@ -110,7 +151,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
   const int d = blockIdx.x / p.NT, tile = blockIdx.x % p.NT, u0 = tile * UT;
   const int NK = H / BK;
   const int GH = G * H;
-  unsigned int* bar = p.bar + d;
+  unsigned int* ctr = p.bar + 32 * d;   // one 128-byte line per direction
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmW[d]);
@@ -121,11 +162,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
   }
   for (int i = threadIdx.x; i < UT * NBp; i += THREADS) cst[i] = 0.f;
   if (warp == 1) {
-    // TMEM columns: power of two >= max(32, NB)
-    if (NB <= 32) tmem_alloc<32>(tmem_slot);
-    else if (NB <= 64) tmem_alloc<64>(tmem_slot);
-    else if (NB <= 128) tmem_alloc<128>(tmem_slot);
-    else tmem_alloc<256>(tmem_slot);
+    tmem_alloc<512>(tmem_slot);
   }
   tc_fence_before();
   __syncthreads();
@@ -135,51 +172,51 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
 
   if (warp == 0) {
     if (lane == 0) {
-      // two cursors over the chunk sequence (steps 1..T-1, NK chunks each): weights run ahead of the barrier
-      const long long total = (long long)(T - 1) * NK;
-      long long wc = 0, ac = 0;
-      while (ac < total) {
-        while (wc < total && wc - ac < STAGES) {
-          const int s = (int)(wc % STAGES);
-          const uint32_t ph = (uint32_t)((wc / STAGES) & 1);
-          if (!mbar_try_wait(&empty[s], ph ^ 1)) break;
+      // strict chunk order: slot free -> weight chunk -> (first chunk of a step: grid barrier) -> h chunk.
+      // The weight chunk of the next step's first slot is therefore in flight while the barrier is awaited.
+      int s = 0;
+      uint32_t ph = 0;
+      for (int step = 1; step < T; ++step) {
+        const int t = d == 0 ? step : T - 1 - step;
+        const int tp = d == 0 ? t - 1 : t + 1;
+        for (int c = 0; c < NK; ++c) {
+          mbar_wait(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], tx_bytes);
-          tma_load_3d(smem + s * STAGE_BYTES, &p.tmW[d], &full[s], (int)(wc % NK) * BK, u0, 0);
-          ++wc;
-        }
-        if (wc > ac) {
-          const int step = 1 + (int)(ac / NK), c = (int)(ac % NK);
-          const int t = d == 0 ? step : T - 1 - step;
-          const int tp = d == 0 ? t - 1 : t + 1;
+          tma_load_3d(smem + s * STAGE_BYTES, &p.tmW[d], &full[s], c * BK, u0, 0);
           if (c == 0) {
-            grid_wait(bar, (unsigned int)p.NT * (unsigned int)step, p.err);
+            grid_wait_counter(ctr, (unsigned int)p.NT * (unsigned int)step, p.err);
             fence_proxy_async_all();
             trace_stamp(p.trace, step, 0);
           }
-          const int s = (int)(ac % STAGES);
           tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &p.tmV[d], &full[s], c * BK, tp * B);
-          ++ac;
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      // The single issuing thread is the critical path of a step (measured: ~69 cycles per tcgen05.mma even
+      // in a minimal loop, ~280 with per-MMA descriptor arithmetic): keep the loop free of div/mod and
+      // descriptor construction.
       const uint32_t idesc = instr_desc(FMT_TF32, MM, NB);
-      long long ch = 0;
+      const uint64_t a_base = smem_desc_sw128(smem_u32(smem));
+      const uint64_t b_base = smem_desc_sw128(smem_u32(smem + A_BYTES));
+      const uint64_t stage_step = (uint64_t)(STAGE_BYTES >> 4);
+      int s = 0;
+      uint32_t ph = 0;
       for (int step = 1; step < T; ++step) {
-        for (int c = 0; c < NK; ++c, ++ch) {
-          const int s = (int)(ch % STAGES);
-          const uint32_t ph = (uint32_t)((ch / STAGES) & 1);
+        for (int c = 0; c < NK; ++c) {
           mbar_wait(&full[s], ph);
           if (c == 0) trace_stamp(p.trace, step, 1);
           if (c == NK - 1) trace_stamp(p.trace, step, 2);
           tc_fence_after();
-          const uint64_t adesc = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES));
-          const uint64_t bdesc = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES));
-#pragma unroll
-          for (int k = 0; k < BK / 8; ++k)
-            mma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (c | k) != 0);
+          const uint64_t ad = a_base + (uint64_t)s * stage_step, bd = b_base + (uint64_t)s * stage_step;
+          mma_tf32(tmem_base, ad, bd, idesc, c > 0);
+          mma_tf32(tmem_base, ad + 2, bd + 2, idesc, 1);
+          mma_tf32(tmem_base, ad + 4, bd + 4, idesc, 1);
+          mma_tf32(tmem_base, ad + 6, bd + 6, idesc, 1);
           mma_commit(&empty[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         mma_commit(accum_bar);
       }
@@ -210,7 +247,14 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
         float acc[32];
         if (step > 0 && q < G) {
           if (cb == 0) { mbar_wait(accum_bar, acc_phase); tc_fence_after(); if (e == 0) trace_stamp(p.trace, step, 3); }
+          const int nsum = min(p.nacc, NK * (BK / 8));
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, acc);
+          for (int a2 = 1; a2 < nsum; ++a2) {
+            float part[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a2 * p.acc_cols + cb), part);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] += part[j];
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[j] = 0.f;
@@ -223,13 +267,13 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
             float v;
             if (RNN == DS2_RNN_LSTM) {
               float pre = gx[j] + bias_x + acc[j] + bias_h;
-              v = (q == 2) ? tanhf(pre) : sigmoidf_(pre);
+              v = (q == 2) ? fast_tanh(pre) : fast_sigmoid(pre);
             } else if (RNN == DS2_RNN_GRU) {
-              if (q < 2) v = sigmoidf_(gx[j] + bias_x + acc[j] + bias_h);
+              if (q < 2) v = fast_sigmoid(gx[j] + bias_x + acc[j] + bias_h);
               else if (q == 2) v = acc[j] + bias_h;          // W_hn h + b_hn
               else v = gx[j] + bias_xn;                      // x_n + b_in
             } else {
-              v = (q == 0) ? tanhf(gx[j] + bias_x + acc[j] + bias_h) : 0.f;
+              v = (q == 0) ? fast_tanh(gx[j] + bias_x + acc[j] + bias_h) : 0.f;
             }
             ex[(q * UT + lane) * NBp + b] = v;
           }
@@ -252,7 +296,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
           float cval = 0.f;
           if (valid) {
             cval = fmaf(e1, cst[ui * NBp + b], e0 * e2);
-            hval = e3 * tanhf(cval);
+            hval = e3 * fast_tanh(cval);
             cst[ui * NBp + b] = cval;
           }
           p.aux[so] = cval;
@@ -264,7 +308,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
           float nval = 0.f;
           if (valid) {
             const float hprev = cst[ui * NBp + b];
-            nval = tanhf(fmaf(e0, e2, e3));
+            nval = fast_tanh(fmaf(e0, e2, e3));
             hval = fmaf(e1, hprev - nval, nval);
             cst[ui * NBp + b] = hval;
           }
@@ -276,19 +320,19 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
         }
         p.hseq[so] = hval;
       }
-      __threadfence();
-      fence_proxy_async_all();
-      named_bar_sync(1, 128);
-      if (e == 0) { red_release(bar, 1u); trace_stamp(p.trace, step, 5); }
+      named_bar_sync(1, 128);          // CTA-scope: every epilogue thread's stores happen-before thread 0's release
+      if (e == 0) {
+        __threadfence();
+        fence_proxy_async_all();
+        red_release(ctr, 1u);
+        trace_stamp(p.trace, step, 5);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    if (NB <= 32) tmem_dealloc<32>(tmem_base);
-    else if (NB <= 64) tmem_dealloc<64>(tmem_base);
-    else if (NB <= 128) tmem_dealloc<128>(tmem_base);
-    else tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -305,7 +349,15 @@ static size_t fwd_smem_bytes(int NB) {
          (2 * STAGES + 2) * sizeof(uint64_t) + 64;
 }
 
-size_t rnn_sweep_tc_workspace_bytes(int, int, int, int, int) { return 1024; }
+size_t rnn_sweep_tc_workspace_bytes(int, int, int, int, int) { return 4096; }
+
+static void set_acc_layout(PersistParams& p) {
+  // accumulator width = power of two >= max(32, NB) columns; as many chains as fit in the 512 TMEM columns
+  int cols = 32;
+  while (cols < p.NB) cols *= 2;
+  p.acc_cols = cols;
+  p.nacc = 1;   // one chain: switching accumulators between MMAs was measured slower, not faster
+}
 
 static bool fwd_eligible(const SeqArgs& a) {
   if (a.h0 || a.c0) return false;                 // initial states -> generic step kernels
@@ -322,9 +374,10 @@ static int launch_fwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t 
   p.training = a.training;
   p.len = a.len; p.gates = a.gates; p.hseq = a.hseq; p.aux = a.aux;
   p.trace = trace_ptr_from_env("DS2_TRACE_FWD");
-  if (ws_bytes < 1024) return 1;
-  p.bar = static_cast<unsigned int*>(ws);
-  p.err = reinterpret_cast<int*>(static_cast<char*>(ws) + 64);
+  if (ws_bytes < 4096) return 1;
+  set_acc_layout(p);
+  p.err = static_cast<int*>(ws);
+  p.bar = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + 128);
   const size_t smem = fwd_smem_bytes(p.NB);
   auto kern = rnn_fwd_persist_kernel<RNN>;
   static bool attr_done = false;
@@ -348,7 +401,7 @@ static int launch_fwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t 
     rc = make_tmap_2d(&p.tmV[d], a.hseq + (size_t)d * a.T * a.B * a.H, a.T * a.B, a.H, a.H, a.B, BK);
     if (rc) return rc;
   }
-  DS2_CHECK_CUDA(cudaMemsetAsync(ws, 0, 128, st));
+  DS2_CHECK_CUDA(cudaMemsetAsync(ws, 0, 4096, st));
   void* args[] = {&p};
   DS2_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(THREADS), args, smem, st));
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -391,7 +444,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
   const int d = blockIdx.x / p.NT, tile = blockIdx.x % p.NT, u0 = tile * UT;
   const int GH = G * H;
   const int NK = GH / BK;
-  unsigned int* bar = p.bar + d;
+  unsigned int* ctr = p.bar + 32 * d;   // one 128-byte line per direction
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmW[d]);
@@ -402,10 +455,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
   }
   for (int i = threadIdx.x; i < UT * NBp; i += THREADS) { cst[i] = 0.f; ex[i] = 0.f; }
   if (warp == 1) {
-    if (NB <= 32) tmem_alloc<32>(tmem_slot);
-    else if (NB <= 64) tmem_alloc<64>(tmem_slot);
-    else if (NB <= 128) tmem_alloc<128>(tmem_slot);
-    else tmem_alloc<256>(tmem_slot);
+    tmem_alloc<512>(tmem_slot);
   }
   tc_fence_before();
   __syncthreads();
@@ -415,54 +465,53 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
 
   if (warp == 0) {
     if (lane == 0) {
-      const long long total = (long long)(T - 1) * NK;
-      long long wc = 0, ac = 0;
-      while (ac < total) {
-        while (wc < total && wc - ac < STAGES) {
-          const int s = (int)(wc % STAGES);
-          const uint32_t ph = (uint32_t)((wc / STAGES) & 1);
-          if (!mbar_try_wait(&empty[s], ph ^ 1)) break;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int step = 1; step < T; ++step) {
+        const int t = d == 0 ? T - 1 - step : step;
+        const int tn = d == 0 ? t + 1 : t - 1;
+        for (int c = 0; c < NK; ++c) {
+          mbar_wait(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], tx_bytes);
-          tma_load_2d(smem + s * STAGE_BYTES, &p.tmW[d], &full[s], (int)(wc % NK) * BK, u0);
-          ++wc;
-        }
-        if (wc > ac) {
-          const int step = 1 + (int)(ac / NK), c = (int)(ac % NK);
-          const int t = d == 0 ? T - 1 - step : step;
-          const int tn = d == 0 ? t + 1 : t - 1;
+          tma_load_2d(smem + s * STAGE_BYTES, &p.tmW[d], &full[s], c * BK, u0);
           if (c == 0) {
-            grid_wait(bar, (unsigned int)p.NT * (unsigned int)step, p.err);
+            grid_wait_counter(ctr, (unsigned int)p.NT * (unsigned int)step, p.err);
             fence_proxy_async_all();
             trace_stamp(p.trace, step, 0);
           }
-          const int s = (int)(ac % STAGES);
           const int k0 = c * BK;
           if (RNN == DS2_RNN_GRU && k0 >= 2 * H)
             tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &p.tmV2[d], &full[s], k0 - 2 * H, tn * B);
           else
             tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &p.tmV[d], &full[s], d * GH + k0, tn * B);
-          ++ac;
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      // The single issuing thread is the critical path of a step (measured: ~69 cycles per tcgen05.mma even
+      // in a minimal loop, ~280 with per-MMA descriptor arithmetic): keep the loop free of div/mod and
+      // descriptor construction.
       const uint32_t idesc = instr_desc(FMT_TF32, MM, NB);
-      long long ch = 0;
+      const uint64_t a_base = smem_desc_sw128(smem_u32(smem));
+      const uint64_t b_base = smem_desc_sw128(smem_u32(smem + A_BYTES));
+      const uint64_t stage_step = (uint64_t)(STAGE_BYTES >> 4);
+      int s = 0;
+      uint32_t ph = 0;
       for (int step = 1; step < T; ++step) {
-        for (int c = 0; c < NK; ++c, ++ch) {
-          const int s = (int)(ch % STAGES);
-          const uint32_t ph = (uint32_t)((ch / STAGES) & 1);
+        for (int c = 0; c < NK; ++c) {
           mbar_wait(&full[s], ph);
           if (c == 0) trace_stamp(p.trace, step, 1);
           if (c == NK - 1) trace_stamp(p.trace, step, 2);
           tc_fence_after();
-          const uint64_t adesc = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES));
-          const uint64_t bdesc = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES));
-#pragma unroll
-          for (int k = 0; k < BK / 8; ++k)
-            mma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (c | k) != 0);
+          const uint64_t ad = a_base + (uint64_t)s * stage_step, bd = b_base + (uint64_t)s * stage_step;
+          mma_tf32(tmem_base, ad, bd, idesc, c > 0);
+          mma_tf32(tmem_base, ad + 2, bd + 2, idesc, 1);
+          mma_tf32(tmem_base, ad + 4, bd + 4, idesc, 1);
+          mma_tf32(tmem_base, ad + 6, bd + 6, idesc, 1);
           mma_commit(&empty[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         mma_commit(accum_bar);
       }
@@ -481,7 +530,14 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
         if (lane == 0) trace_stamp(p.trace, step, 3);
         for (int cb = 0; cb < NB; cb += 32) {
           float acc[32];
+          const int nsum = min(p.nacc, NK * (BK / 8));
           tmem_ld32(tmem_base + (uint32_t)cb, acc);
+          for (int a2 = 1; a2 < nsum; ++a2) {
+            float part[32];
+            tmem_ld32(tmem_base + (uint32_t)(a2 * p.acc_cols + cb), part);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] += part[j];
+          }
           if (lane < UT) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -524,19 +580,19 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
           }
         }
       }
-      __threadfence();
-      fence_proxy_async_all();
-      named_bar_sync(1, 128);
-      if (e == 0) { red_release(bar, 1u); trace_stamp(p.trace, step, 5); }
+      named_bar_sync(1, 128);          // CTA-scope: every epilogue thread's stores happen-before thread 0's release
+      if (e == 0) {
+        __threadfence();
+        fence_proxy_async_all();
+        red_release(ctr, 1u);
+        trace_stamp(p.trace, step, 5);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    if (NB <= 32) tmem_dealloc<32>(tmem_base);
-    else if (NB <= 64) tmem_dealloc<64>(tmem_base);
-    else if (NB <= 128) tmem_dealloc<128>(tmem_base);
-    else tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -550,9 +606,10 @@ static int launch_bwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t 
   p.training = 1;
   p.len = a.len; p.gates = a.gates; p.hseq = a.hseq; p.aux = a.aux; p.dy = a.dy;
   p.trace = trace_ptr_from_env("DS2_TRACE_BWD");
-  if (ws_bytes < 1024) return 1;
-  p.bar = static_cast<unsigned int*>(ws);
-  p.err = reinterpret_cast<int*>(static_cast<char*>(ws) + 64);
+  if (ws_bytes < 4096) return 1;
+  set_acc_layout(p);
+  p.err = static_cast<int*>(ws);
+  p.bar = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + 128);
   const size_t smem = fwd_smem_bytes(p.NB);
   auto kern = rnn_bwd_persist_kernel<RNN>;
   static bool attr_done = false;
@@ -581,7 +638,7 @@ static int launch_bwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t 
       if (rc) return rc;
     }
   }
-  DS2_CHECK_CUDA(cudaMemsetAsync(ws, 0, 128, st));
+  DS2_CHECK_CUDA(cudaMemsetAsync(ws, 0, 4096, st));
   void* args[] = {&p};
   DS2_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(THREADS), args, smem, st));
   g_launches.fetch_add(1, std::memory_order_relaxed);
