@@ -41,10 +41,19 @@ def log(msg):
 
 
 def host_cores():
+    """usable host cores: min(affinity mask, cgroup cpu quota) — the GPU boxes expose 128 logical CPUs but the
+    container is limited to a quota (cpu.max), and oversubscribing torch's thread pool makes the CPU path crawl"""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
 
 
 def load_peaks():

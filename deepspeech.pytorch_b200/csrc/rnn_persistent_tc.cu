@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
   const int NBp = NB + 1;
   float* ex = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);   // [4][UT][NBp]
   float* cst = ex + 4 * UT * NBp;                                       // [UT][NBp] cell (LSTM) / hidden (GRU) state
-  uint64_t* full = reinterpret_cast<uint64_t*>(cst + UT * NBp + ((UT * NBp) & 1));
+  int* lens_s = reinterpret_cast<int*>(cst + UT * NBp);                 // [NB] (padded to even)
+  uint64_t* full = reinterpret_cast<uint64_t*>(lens_s + ((NB + 1) & ~1));
   uint64_t* empty = full + STAGES;
   uint64_t* accum_bar = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < UT * NBp; i += THREADS) cst[i] = 0.f;
+  for (int i = threadIdx.x; i < NB; i += THREADS) lens_s[i] = i < B ? p.len[i] : 0;
   if (warp == 1) {
     tmem_alloc<512>(tmem_slot);
   }
@@ -223,60 +225,57 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
     }
   } else {
     // ---------------- epilogue warps: quarter q of TMEM == gate q (rows q*16 .. q*16+15 in lanes 0..15)
+    // All 32 lanes work: lane L<16 owns row (q, L); its 32 batch columns are split with lane L+16
+    // (columns 16..31 travel by shuffle), so every lane activates 16 values per 32-column chunk.
     const int q = warp % 4;
     const int e = threadIdx.x - 64;          // 0..127
-    const bool act_lane = lane < UT;
-    const int u = u0 + lane;                 // valid when act_lane
-    float bias_x = 0.f, bias_h = 0.f;        // b_ih / b_hh of this thread's (gate q, unit u)
-    if (act_lane && q < G) { bias_x = p.b_ih[d][q * H + u]; bias_h = p.b_hh[d][q * H + u]; }
-    float bias_xn = 0.f;                     // GRU: warp 3 carries x_n + b_in
-    if (RNN == DS2_RNN_GRU && act_lane && q == 3) bias_xn = p.b_ih[d][2 * H + u];
+    const int ul = lane & 15, half = lane >> 4;
+    const int u = u0 + ul;
+    const bool has_row = (q < G) || (RNN == DS2_RNN_GRU && q == 3);
+    const int gsel = (RNN == DS2_RNN_GRU && q == 3) ? 2 : q;   // GRU: warp 3 carries x_n + b_in
+    float bias_x = 0.f, bias_h = 0.f;
+    if (has_row) bias_x = p.b_ih[d][gsel * H + u];
+    if (q < G) bias_h = p.b_hh[d][q * H + u];
     uint32_t acc_phase = 0;
     for (int step = 0; step < T; ++step) {
       const int t = d == 0 ? step : T - 1 - step;
-      // input-projection values of this thread for every batch column (independent of the recurrence)
       for (int cb = 0; cb < NB; cb += 32) {
-        float gx[32];
-        const int gsel = (RNN == DS2_RNN_GRU && q == 3) ? 2 : q;
-        const bool need_gx = act_lane && (q < G || (RNN == DS2_RNN_GRU && q == 3));
+        // input-projection values (independent of the recurrence: issued before waiting for the MMAs)
+        float gx[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int b = cb + j;
-          gx[j] = (need_gx && b < B) ? p.gates[(((size_t)t * B + b) * D + d) * GH + (size_t)gsel * H + u] : 0.f;
+        for (int j = 0; j < 16; ++j) {
+          const int b = cb + half * 16 + j;
+          gx[j] = (has_row && b < B) ? p.gates[(((size_t)t * B + b) * D + d) * GH + (size_t)gsel * H + u] : 0.f;
         }
-        float acc[32];
+        float a16[16];
         if (step > 0 && q < G) {
           if (cb == 0) { mbar_wait(accum_bar, acc_phase); tc_fence_after(); if (e == 0) trace_stamp(p.trace, step, 3); }
-          const int nsum = min(p.nacc, NK * (BK / 8));
+          float acc[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, acc);
-          for (int a2 = 1; a2 < nsum; ++a2) {
-            float part[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a2 * p.acc_cols + cb), part);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] += part[j];
+          for (int j = 0; j < 16; ++j) {
+            const float hi = __shfl_sync(0xffffffffu, acc[16 + j], ul);   // row owner's upper columns
+            a16[j] = half ? hi : acc[j];
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+          for (int j = 0; j < 16; ++j) a16[j] = 0.f;
         }
-        if (act_lane) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int b = cb + j;
-            if (b >= B) break;
-            float v;
-            if (RNN == DS2_RNN_LSTM) {
-              float pre = gx[j] + bias_x + acc[j] + bias_h;
-              v = (q == 2) ? fast_tanh(pre) : fast_sigmoid(pre);
-            } else if (RNN == DS2_RNN_GRU) {
-              if (q < 2) v = fast_sigmoid(gx[j] + bias_x + acc[j] + bias_h);
-              else if (q == 2) v = acc[j] + bias_h;          // W_hn h + b_hn
-              else v = gx[j] + bias_xn;                      // x_n + b_in
-            } else {
-              v = (q == 0) ? fast_tanh(gx[j] + bias_x + acc[j] + bias_h) : 0.f;
-            }
-            ex[(q * UT + lane) * NBp + b] = v;
+        for (int j = 0; j < 16; ++j) {
+          const int b = cb + half * 16 + j;
+          float v;
+          if (RNN == DS2_RNN_LSTM) {
+            const float pre = gx[j] + bias_x + a16[j] + bias_h;
+            v = (q == 2) ? fast_tanh(pre) : fast_sigmoid(pre);
+          } else if (RNN == DS2_RNN_GRU) {
+            if (q < 2) v = fast_sigmoid(gx[j] + bias_x + a16[j] + bias_h);
+            else if (q == 2) v = a16[j] + bias_h;          // W_hn h + b_hn
+            else v = gx[j] + bias_x;                       // x_n + b_in
+          } else {
+            v = (q == 0) ? fast_tanh(gx[j] + bias_x + a16[j] + bias_h) : 0.f;
           }
+          if (b < B) ex[(q * UT + ul) * NBp + b] = v;
         }
       }
       if (step > 0) acc_phase ^= 1;
@@ -286,7 +285,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
       // ---------------- combine: (unit, batch) pairs over the 128 epilogue threads
       for (int pi = e; pi < UT * B; pi += 128) {
         const int ui = pi % UT, b = pi / UT;
-        const bool valid = t < p.len[b];
+        const bool valid = t < lens_s[b];
         const size_t so = (((size_t)d * T + t) * B + b) * H + u0 + ui;
         float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + ui;
         const float e0 = ex[(0 * UT + ui) * NBp + b], e1 = ex[(1 * UT + ui) * NBp + b];
@@ -322,9 +321,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
       }
       named_bar_sync(1, 128);          // CTA-scope: every epilogue thread's stores happen-before thread 0's release
       if (e == 0) {
-        __threadfence();
         fence_proxy_async_all();
-        red_release(ctr, 1u);
+        red_release(ctr, 1u);            // release is cumulative over the stores ordered by the named barrier
         trace_stamp(p.trace, step, 5);
       }
     }
@@ -345,7 +343,7 @@ static long long* trace_ptr_from_env(const char* name) {
 static size_t fwd_smem_bytes(int NB) {
   using namespace rp;
   size_t NBp = NB + 1;
-  return 1024 + (size_t)STAGES * (A_BYTES + (size_t)NB * 128) + (5 * UT * NBp + 2) * sizeof(float) +
+  return 1024 + (size_t)STAGES * (A_BYTES + (size_t)NB * 128) + (5 * UT * NBp + NB + 4) * sizeof(float) +
          (2 * STAGES + 2) * sizeof(uint64_t) + 64;
 }
 
@@ -582,9 +580,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
       }
       named_bar_sync(1, 128);          // CTA-scope: every epilogue thread's stores happen-before thread 0's release
       if (e == 0) {
-        __threadfence();
         fence_proxy_async_all();
-        red_release(ctr, 1u);
+        red_release(ctr, 1u);            // release is cumulative over the stores ordered by the named barrier
         trace_stamp(p.trace, step, 5);
       }
     }
@@ -594,6 +591,299 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
   if (warp == 1) {
     tmem_dealloc<512>(tmem_base);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward sweep, split-K variant (the fast path): a 4-CTA cluster owns 64 hidden units; CTA `ks` of
+// the cluster reduces over a quarter of K = G*H, so every CTA issues the same number of MMAs per
+// step as the forward sweep with all 64 M rows useful.  The partial sums (64 units x B) are exchanged
+// through distributed shared memory: each CTA publishes its partial tile, signals the four cluster
+// peers' mbarriers (release.cluster) and then reduces + finishes the 16 units it owns (gate backward,
+// carried dc / dh in shared memory).
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float ld_dsmem(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(tc::smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int RNN>
+__global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __grid_constant__ PersistParams p) {
+  using namespace rp;
+  using namespace tc;
+  constexpr int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
+  constexpr int UM = 64;                       // units per cluster (all M rows valid)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int NB = p.NB, B = p.B, T = p.T, H = p.H, D = p.D;
+  const int B_BYTES = NB * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  const int NBp = NB + 1;
+  float* part = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // [64][NBp] partial dh_rec of this CTA
+  float* cst = part + UM * NBp;                                          // [16][NBp] carried dc / dh
+  int* lens_s = reinterpret_cast<int*>(cst + UT * NBp);
+  uint64_t* full = reinterpret_cast<uint64_t*>(lens_s + ((NB + 1) & ~1));
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum_bar = empty + STAGES;
+  uint64_t* part_bar = accum_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(part_bar + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int ks = blockIdx.x & 3;                          // rank in the cluster == K split
+  const int cl = blockIdx.x >> 2;
+  const int NTc = H / UM;                                 // clusters per direction
+  const int d = cl / NTc, ut = cl % NTc;
+  const int GH = G * H;
+  const int Kc = GH / 4, NK = Kc / BK;
+  const int kbase = ks * Kc;
+  const int u0 = ut * UM + ks * UT;                       // the 16 units this CTA finishes
+  unsigned int* ctr = p.bar + 32 * d;
+  const unsigned int n_arrive = (unsigned int)(NTc * 4);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmW[d]);
+    tma_prefetch_desc(&p.tmV[d]);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(accum_bar, 1);
+    mbar_init(part_bar, 4);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < UT * NBp; i += THREADS) cst[i] = 0.f;
+  for (int i = threadIdx.x; i < NB; i += THREADS) lens_s[i] = i < B ? p.len[i] : 0;
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_all();                                     // peers' mbarriers are initialised
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tx_bytes = (uint32_t)(UM * 128 + B * 128);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int step = 1; step < T; ++step) {
+        const int t = d == 0 ? T - 1 - step : step;
+        const int tn = d == 0 ? t + 1 : t - 1;
+        for (int c = 0; c < NK; ++c) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], tx_bytes);
+          const int k0 = kbase + c * BK;
+          tma_load_2d(smem + s * STAGE_BYTES, &p.tmW[d], &full[s], k0, ut * UM);
+          if (c == 0) {
+            grid_wait_counter(ctr, n_arrive * (unsigned int)step, p.err);
+            fence_proxy_async_all();
+            trace_stamp(p.trace, step, 0);
+          }
+          if (RNN == DS2_RNN_GRU && k0 >= 2 * H)
+            tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &p.tmV2[d], &full[s], k0 - 2 * H, tn * B);
+          else
+            tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &p.tmV[d], &full[s], d * GH + k0, tn * B);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(FMT_TF32, MM, NB);
+      const uint64_t a_base = smem_desc_sw128(smem_u32(smem));
+      const uint64_t b_base = smem_desc_sw128(smem_u32(smem + A_BYTES));
+      const uint64_t stage_step = (uint64_t)(STAGE_BYTES >> 4);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int step = 1; step < T; ++step) {
+        for (int c = 0; c < NK; ++c) {
+          mbar_wait(&full[s], ph);
+          if (c == 0) trace_stamp(p.trace, step, 1);
+          if (c == NK - 1) trace_stamp(p.trace, step, 2);
+          tc_fence_after();
+          const uint64_t ad = a_base + (uint64_t)s * stage_step, bd = b_base + (uint64_t)s * stage_step;
+          mma_tf32(tmem_base, ad, bd, idesc, c > 0);
+          mma_tf32(tmem_base, ad + 2, bd + 2, idesc, 1);
+          mma_tf32(tmem_base, ad + 4, bd + 4, idesc, 1);
+          mma_tf32(tmem_base, ad + 6, bd + 6, idesc, 1);
+          mma_commit(&empty[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        mma_commit(accum_bar);
+      }
+    }
+  } else {
+    const int q = warp % 4;
+    const int e = threadIdx.x - 64;
+    const int ul = lane & 15, half = lane >> 4;
+    uint32_t acc_phase = 0, part_phase = 0;
+    const uint32_t part_local = smem_u32(part);
+    uint32_t part_remote[4], bar_remote[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      part_remote[r] = mapa_u32(part_local, (uint32_t)r);
+      bar_remote[r] = mapa_u32(smem_u32(part_bar), (uint32_t)r);
+    }
+    for (int step = 0; step < T; ++step) {
+      const int t = d == 0 ? T - 1 - step : step;
+      const int tp = d == 0 ? t - 1 : t + 1;
+      const bool tp_in = tp >= 0 && tp < T;
+      if (step > 0) {
+        // publish this CTA's partial tile: row (16q + ul), 32 columns split over the two half-warps
+        mbar_wait(accum_bar, acc_phase);
+        tc_fence_after();
+        if (e == 0) trace_stamp(p.trace, step, 3);
+        for (int cb = 0; cb < NB; cb += 32) {
+          float acc[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, acc);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float hi = __shfl_sync(0xffffffffu, acc[16 + j], ul);
+            const float v = half ? hi : acc[j];
+            const int b = cb + half * 16 + j;
+            if (b < B) part[(q * 16 + ul) * NBp + b] = v;
+          }
+        }
+        acc_phase ^= 1;
+        tc_fence_before();
+        named_bar_sync(1, 128);
+        if (e < 4) mbar_arrive_remote(bar_remote[e]);     // release.cluster: the tile is visible to the peer
+        mbar_wait_cluster(part_bar, part_phase);          // all four partial tiles are published
+        part_phase ^= 1;
+      }
+      if (e == 0) trace_stamp(p.trace, step, 4);
+      for (int pi = e; pi < UT * B; pi += 128) {
+        const int ui = pi % UT, b = pi / UT;
+        const bool valid = t < lens_s[b];
+        const bool pin = tp_in && (d == 0 || tp < lens_s[b]);
+        const size_t si = (((size_t)d * T + t) * B + b) * H + u0 + ui;
+        const size_t sp = (((size_t)d * T + (tp_in ? tp : 0)) * B + b) * H + u0 + ui;
+        float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + ui;
+        if (!valid) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) gp[g * H] = 0.f;
+          if (RNN == DS2_RNN_GRU) p.aux[si] = 0.f;
+        } else {
+          float dh = p.dy[((size_t)t * B + b) * H + u0 + ui];
+          if (step > 0) {
+            const uint32_t off = (uint32_t)(((ks * UT + ui) * NBp + b) * 4);
+            dh += (ld_dsmem(part_remote[0] + off) + ld_dsmem(part_remote[1] + off)) +
+                  (ld_dsmem(part_remote[2] + off) + ld_dsmem(part_remote[3] + off));
+          }
+          if (RNN == DS2_RNN_LSTM) {
+            const float c_prev = pin ? p.aux[sp] : 0.f;
+            LstmBwd r = lstm_cell_bwd(gp[0], gp[H], gp[2 * H], gp[3 * H], p.aux[si], c_prev, dh, cst[ui * NBp + b]);
+            gp[0] = r.di; gp[H] = r.df; gp[2 * H] = r.dg; gp[3 * H] = r.d_o;
+            cst[ui * NBp + b] = r.dc_prev;
+          } else if (RNN == DS2_RNN_GRU) {
+            const float h_prev = pin ? p.hseq[sp] : 0.f;
+            dh += cst[ui * NBp + b];
+            GruBwd r = gru_cell_bwd(gp[0], gp[H], gp[2 * H], p.aux[si], h_prev, dh);
+            gp[0] = r.dr; gp[H] = r.dz; gp[2 * H] = r.dxn;
+            p.aux[si] = r.dhn;
+            cst[ui * NBp + b] = r.dh_prev;
+          } else {
+            const float h = p.hseq[si];
+            gp[0] = dh * (1.f - h * h);
+          }
+        }
+      }
+      named_bar_sync(1, 128);
+      if (e == 0) {
+        fence_proxy_async_all();
+        red_release(ctr, 1u);
+        trace_stamp(p.trace, step, 5);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                     // nobody exits while a peer may still read its tile
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+static size_t splitk_smem_bytes(int NB) {
+  using namespace rp;
+  size_t NBp = NB + 1;
+  return 1024 + (size_t)STAGES * (A_BYTES + (size_t)NB * 128) + ((64 + UT) * NBp + NB + 4) * sizeof(float) +
+         (2 * STAGES + 3) * sizeof(uint64_t) + 64;
+}
+
+template <int RNN>
+static int launch_bwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
+  using namespace rp;
+  const int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
+  const int GH = G * a.H;
+  if (a.H % 64 != 0 || (GH / 4) % BK != 0 || GH % 4 != 0) return 1;
+  PersistParams p{};
+  p.T = a.T; p.B = a.B; p.NB = (a.B + 7) / 8 * 8; p.H = a.H; p.D = a.D; p.NT = a.H / 64; p.G = G;
+  p.training = 1;
+  p.len = a.len; p.gates = a.gates; p.hseq = a.hseq; p.aux = a.aux; p.dy = a.dy;
+  p.trace = trace_ptr_from_env("DS2_TRACE_BWD");
+  if (ws_bytes < 4096) return 1;
+  set_acc_layout(p);
+  p.err = static_cast<int*>(ws);
+  p.bar = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + 128);
+  const size_t smem = splitk_smem_bytes(p.NB);
+  if (smem > 227 * 1024) return 1;
+  auto kern = rnn_bwd_splitk_kernel<RNN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  const int grid = a.D * p.NT * 4;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = 4; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeCooperative;
+  attrs[1].val.cooperative = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 2;
+  int max_clusters = 0;
+  cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+  if (oe != cudaSuccess) { (void)cudaGetLastError(); return 1; }
+  if (max_clusters * 4 < grid) return 1;                 // all clusters must be co-resident (grid barrier)
+  for (int d = 0; d < a.D; ++d) {
+    int rc = make_tmap_2d(&p.tmW[d], a.w_hh[d], a.H, GH, GH, 64, BK);   // W_hh^T (H, G*H): 64 unit rows per box
+    if (rc) return rc;
+    rc = make_tmap_2d(&p.tmV[d], a.gates, a.T * a.B, a.D * GH, a.D * GH, a.B, BK);
+    if (rc) return rc;
+    if (RNN == DS2_RNN_GRU) {
+      rc = make_tmap_2d(&p.tmV2[d], a.aux + (size_t)d * a.T * a.B * a.H, a.T * a.B, a.H, a.H, a.B, BK);
+      if (rc) return rc;
+    }
+  }
+  DS2_CHECK_CUDA(cudaMemsetAsync(ws, 0, 4096, st));
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
+  if (le != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 1;                                            // e.g. cooperative+cluster launch refused: use the 16-unit kernel
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return DS2_OK;
 }
 
 template <int RNN>
@@ -647,6 +937,15 @@ static int launch_bwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t 
 
 int rnn_sweep_bwd_tc(int rnn, const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (a.H % 32 != 0 || a.B > 256 || a.T < 2) return 1;
+  {
+    int rc = 1;
+    if (!getenv("DS2_NO_SPLITK")) {
+      if (rnn == DS2_RNN_LSTM) rc = launch_bwd_splitk<DS2_RNN_LSTM>(a, ws, ws_bytes, st);
+      else if (rnn == DS2_RNN_GRU) rc = launch_bwd_splitk<DS2_RNN_GRU>(a, ws, ws_bytes, st);
+      else rc = launch_bwd_splitk<DS2_RNN_TANH>(a, ws, ws_bytes, st);
+    }
+    if (rc != 1) return rc;   // done or a hard error; 1 = not eligible -> 16-unit kernel below
+  }
   if (rnn == DS2_RNN_LSTM) return launch_bwd<DS2_RNN_LSTM>(a, ws, ws_bytes, st);
   if (rnn == DS2_RNN_GRU) return launch_bwd<DS2_RNN_GRU>(a, ws, ws_bytes, st);
   return launch_bwd<DS2_RNN_TANH>(a, ws, ws_bytes, st);

