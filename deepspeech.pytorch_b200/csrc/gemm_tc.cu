@@ -77,6 +77,26 @@ int make_tmap_3d(CUtensorMap* out, const float* base, int d0, int d1, int d2, si
   return DS2_OK;
 }
 
+// fp16 tensor of rank 2 or 3 (d0 innermost), strides in ELEMENTS, 128B swizzle (box0 * 2 bytes <= 128)
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, int d0, int d1, int d2, size_t stride1,
+                  size_t stride2, int box0, int box1, int box2) {
+  int rc = load_encode();
+  if (rc) return rc;
+  cuuint64_t gdim[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t gstr[2] = {(cuuint64_t)stride1 * 2, (cuuint64_t)stride2 * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, (cuuint32_t)box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(f16 rank %d dims %d,%d,%d box %d,%d,%d) failed: %d", rank, d0, d1, d2, box0, box1,
+              box2, (int)r);
+    return DS2_ERR_CUDA;
+  }
+  return DS2_OK;
+}
+
 // ---- kernel ---------------------------------------------------------------------------------------
 namespace gtc {
 constexpr int BM = 128, BN = 256, BK = 32, STAGES = 4;

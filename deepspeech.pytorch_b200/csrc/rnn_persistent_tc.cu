@@ -18,6 +18,7 @@
 // Backward sweep: the same skeleton on W_hh^T with split-K over the gates inside a 4-CTA cluster
 // (partial sums reduced through distributed shared memory) — see rnn_bwd_persist_kernel.
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -45,6 +46,7 @@ struct PersistParams {
   CUtensorMap tmV2[2];  // bwd GRU: the n-gate part of dGh lives in the aux buffer
   int T, B, NB, H, D, NT, G, training;
   const float* dy;      // bwd: (T,B,H)
+  __half* h16;          // resident fwd: fp16 copy of hseq (D,T,B,H), the MMA operand of the next step
   long long* trace;     // optional: clock64 stamps of CTA 0, 4 per step
   const int32_t* len;
   float* gates;
@@ -130,7 +132,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int RNN>
+// RES = true: "resident" variant.  W_hh is converted to fp16 once per call and this CTA's slice
+// (G*16 rows x H, 128 KB at H=1024) stays in shared memory for the whole sweep; per step only the
+// fp16 copy of h_{t-1} (B x H, 64 KB) is streamed by TMA, and the MMAs are kind::f16 (K=16, half the
+// instruction count).  fp16 has the same 10-bit mantissa as TF32 and |h| < 1, |w| << 65504, so this
+// is the same arithmetic class as the TF32 path (fp32 accumulation in TMEM either way).
+template <int RNN, bool RES>
 __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const __grid_constant__ PersistParams p) {
   using namespace rp;
   using namespace tc;
@@ -140,11 +147,14 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
   const int NB = p.NB, B = p.B, T = p.T, H = p.H, D = p.D;
   const int B_BYTES = NB * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   const int NBp = NB + 1;
-  float* ex = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);   // [4][UT][NBp]
+  const int NKR = H / 64;                                  // resident: 64 fp16 (128 B) of K per chunk
+  // streaming layout: STAGES x (A | B) ; resident layout: NKR x A (weights) then NKR x B (h chunks)
+  const int ring_bytes = RES ? NKR * STAGE_BYTES : STAGES * STAGE_BYTES;
+  float* ex = reinterpret_cast<float*>(smem + ring_bytes);            // [4][UT][NBp]
   float* cst = ex + 4 * UT * NBp;                                       // [UT][NBp] cell (LSTM) / hidden (GRU) state
   int* lens_s = reinterpret_cast<int*>(cst + UT * NBp);                 // [NB] (padded to even)
-  uint64_t* full = reinterpret_cast<uint64_t*>(lens_s + ((NB + 1) & ~1));
-  uint64_t* empty = full + STAGES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(lens_s + ((NB + 1) & ~1));   // resident: one per h chunk (<= 32)
+  uint64_t* empty = full + (RES ? 32 : STAGES);                             // resident: [0] = weights landed
   uint64_t* accum_bar = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
@@ -157,7 +167,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmW[d]);
     tma_prefetch_desc(&p.tmV[d]);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < (RES ? 32 : STAGES); ++i) mbar_init(&full[i], 1);
+    for (int i = 0; i < STAGES; ++i) mbar_init(&empty[i], 1);
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
@@ -170,9 +181,39 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // The CTA owns all 512 TMEM columns, so the allocation starts at address 0.  Using the literal keeps the
+  // accumulator operand of tcgen05.mma in a uniform register without the ELECT / R2UR.BROADCAST waterfall
+  // loop nvcc otherwise emits per MMA for a value it cannot prove warp-uniform.
+  if (tmem_base != 0 && threadIdx.x == 0) {
+    *(volatile int*)p.err = 2;
+    printf("ds2: unexpected TMEM base %u (block %d)\n", tmem_base, blockIdx.x);
+  }
   const uint32_t tx_bytes = (uint32_t)(G * UT * 128 + B * 128);
 
   if (warp == 0) {
+    if (RES) {
+      if (lane == 0) {
+        // weights once: NKR chunks of (G*16 rows x 64 fp16) into the resident region
+        mbar_arrive_expect_tx(&empty[0], (uint32_t)(NKR * G * UT * 128));
+        for (int c = 0; c < NKR; ++c) tma_load_3d(smem + c * A_BYTES, &p.tmW[d], &empty[0], c * 64, u0, 0);
+        uint8_t* hbuf = smem + NKR * A_BYTES;
+        for (int step = 1; step < T; ++step) {
+          const int t = d == 0 ? step : T - 1 - step;
+          const int tp = d == 0 ? t - 1 : t + 1;
+          // the previous step's MMAs have finished reading hbuf: this CTA's epilogue (which waited for them)
+          // arrived at the barrier we are about to pass
+          grid_wait_counter(ctr, (unsigned int)p.NT * (unsigned int)step, p.err);
+          fence_proxy_async_all();
+          trace_stamp(p.trace, step, 0);
+          for (int g = 0; g * 4 < NKR; ++g) {  // one mbarrier per group of 4 chunks (256 k)
+            uint64_t* fb = full + g;
+            const int c0 = g * 4, c1 = min(NKR, c0 + 4);
+            mbar_arrive_expect_tx(fb, (uint32_t)((c1 - c0) * B * 128));
+            for (int c = c0; c < c1; ++c) tma_load_2d(hbuf + c * B_BYTES, &p.tmV[d], fb, c * 64, tp * B);
+          }
+        }
+      }
+    } else
     if (lane == 0) {
       // strict chunk order: slot free -> weight chunk -> (first chunk of a step: grid barrier) -> h chunk.
       // The weight chunk of the next step's first slot is therefore in flight while the barrier is awaited.
@@ -196,6 +237,34 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
       }
     }
   } else if (warp == 1) {
+    if (RES) {
+      if (lane == 0) {
+        const uint32_t idesc = instr_desc(FMT_F16, MM, NB);
+        const uint64_t a_base = smem_desc_sw128(smem_u32(smem));
+        const uint64_t b_base = smem_desc_sw128(smem_u32(smem + NKR * A_BYTES));
+        const uint64_t a_step = (uint64_t)(A_BYTES >> 4), b_step = (uint64_t)(B_BYTES >> 4);
+        mbar_wait(&empty[0], 0);                 // weights resident
+        uint32_t ph = 0;
+        for (int step = 1; step < T; ++step) {
+          for (int g = 0; g * 4 < NKR; ++g) {
+            mbar_wait(full + g, ph);
+            tc_fence_after();
+            if (g == 0) trace_stamp(p.trace, step, 1);
+            const int c0 = g * 4, c1 = min(NKR, c0 + 4);
+            if (c1 == NKR) trace_stamp(p.trace, step, 2);
+            for (int c = c0; c < c1; ++c) {
+              const uint64_t ad = a_base + (uint64_t)c * a_step, bd = b_base + (uint64_t)c * b_step;
+              mma_f16(0u, ad, bd, idesc, c > 0);
+              mma_f16(0u, ad + 2, bd + 2, idesc, 1);
+              mma_f16(0u, ad + 4, bd + 4, idesc, 1);
+              mma_f16(0u, ad + 6, bd + 6, idesc, 1);
+            }
+          }
+          mma_commit(accum_bar);
+          ph ^= 1;
+        }
+      }
+    } else
     if (lane == 0) {
       // The single issuing thread is the critical path of a step (measured: ~69 cycles per tcgen05.mma even
       // in a minimal loop, ~280 with per-MMA descriptor arithmetic): keep the loop free of div/mod and
@@ -213,10 +282,10 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
           if (c == NK - 1) trace_stamp(p.trace, step, 2);
           tc_fence_after();
           const uint64_t ad = a_base + (uint64_t)s * stage_step, bd = b_base + (uint64_t)s * stage_step;
-          mma_tf32(tmem_base, ad, bd, idesc, c > 0);
-          mma_tf32(tmem_base, ad + 2, bd + 2, idesc, 1);
-          mma_tf32(tmem_base, ad + 4, bd + 4, idesc, 1);
-          mma_tf32(tmem_base, ad + 6, bd + 6, idesc, 1);
+          mma_tf32(0u, ad, bd, idesc, c > 0);
+          mma_tf32(0u, ad + 2, bd + 2, idesc, 1);
+          mma_tf32(0u, ad + 4, bd + 4, idesc, 1);
+          mma_tf32(0u, ad + 6, bd + 6, idesc, 1);
           mma_commit(&empty[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -318,6 +387,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
           if (p.training) gp[0] = hval;
         }
         p.hseq[so] = hval;
+        if (RES) p.h16[so] = __float2half_rn(hval);
       }
       named_bar_sync(1, 128);          // CTA-scope: every epilogue thread's stores happen-before thread 0's release
       if (e == 0) {
@@ -335,6 +405,11 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
 }
 
 // ------------------------------------------------------------------------------------------------
+// Every persistent CTA allocates all 512 TMEM columns, so two of them must never share an SM (the second
+// tcgen05.alloc would block while the first waits for it at the grid barrier): ask for more than half of
+// the 227 KB of shared memory even when the tiles are small.
+static size_t one_cta_per_sm(size_t smem) { return smem < 116 * 1024 ? 116 * 1024 : smem; }
+
 static long long* trace_ptr_from_env(const char* name) {
   const char* e = getenv(name);   // debug: device address of an int64 buffer of 6*T entries
   return e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 10)) : nullptr;
@@ -347,7 +422,10 @@ static size_t fwd_smem_bytes(int NB) {
          (2 * STAGES + 2) * sizeof(uint64_t) + 64;
 }
 
-size_t rnn_sweep_tc_workspace_bytes(int, int, int, int, int) { return 4096; }
+size_t rnn_sweep_tc_workspace_bytes(int rnn, int T, int B, int H, int D) {
+  const int G = rnn == DS2_RNN_LSTM ? 4 : (rnn == DS2_RNN_GRU ? 3 : 1);
+  return 4096 + align_up((size_t)D * G * H * H * 2, 256) + align_up((size_t)D * T * B * H * 2, 256) + 256;
+}
 
 static void set_acc_layout(PersistParams& p) {
   // accumulator width = power of two >= max(32, NB) columns; as many chains as fit in the 512 TMEM columns
@@ -363,10 +441,80 @@ static bool fwd_eligible(const SeqArgs& a) {
   return true;
 }
 
+__global__ void f32_to_f16_kernel(size_t n, const float* __restrict__ in, __half* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = __float2half_rn(in[i]);
+}
+
+static size_t res_smem_bytes(int NB, int H) {
+  using namespace rp;
+  size_t NBp = NB + 1;
+  return 1024 + (size_t)(H / 64) * (A_BYTES + (size_t)NB * 128) + (5 * UT * NBp + NB + 4) * sizeof(float) +
+         (32 + STAGES + 2) * sizeof(uint64_t) + 64;
+}
+
+// workspace of the resident forward: [4 KB control][W16: D*G*H*H halfs][h16: D*T*B*H halfs]
+static size_t res_ws_bytes(int G, int T, int B, int H, int D) {
+  return 4096 + align_up((size_t)D * G * H * H * 2, 256) + align_up((size_t)D * T * B * H * 2, 256);
+}
+
+template <int RNN>
+static int launch_fwd_resident(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
+  using namespace rp;
+  const int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
+  if (a.H % 64 != 0 || a.H / 64 > 32) return 1;
+  if (ws_bytes < res_ws_bytes(G, a.T, a.B, a.H, a.D)) return 1;
+  PersistParams p{};
+  p.T = a.T; p.B = a.B; p.NB = (a.B + 7) / 8 * 8; p.H = a.H; p.D = a.D; p.NT = a.H / UT; p.G = G;
+  p.training = a.training;
+  p.len = a.len; p.gates = a.gates; p.hseq = a.hseq; p.aux = a.aux;
+  p.trace = trace_ptr_from_env("DS2_TRACE_FWD");
+  set_acc_layout(p);
+  p.err = static_cast<int*>(ws);
+  p.bar = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + 128);
+  __half* w16 = reinterpret_cast<__half*>(static_cast<char*>(ws) + 4096);
+  p.h16 = reinterpret_cast<__half*>(static_cast<char*>(ws) + 4096 + align_up((size_t)a.D * G * a.H * a.H * 2, 256));
+  const size_t smem = one_cta_per_sm(res_smem_bytes(p.NB, a.H));
+  if (smem > 227 * 1024) return 1;
+  auto kern = rnn_fwd_persist_kernel<RNN, true>;
+  static bool attr_done = false;
+  static int num_sms = 0;
+  if (!attr_done) {
+    DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int dev = 0;
+    DS2_CHECK_CUDA(cudaGetDevice(&dev));
+    DS2_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_done = true;
+  }
+  int max_blocks_per_sm = 0;
+  DS2_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, kern, THREADS, smem));
+  const int grid = a.D * p.NT;
+  if (max_blocks_per_sm < 1 || grid > max_blocks_per_sm * num_sms) return 1;
+  const size_t wn = (size_t)G * a.H * a.H;
+  for (int d = 0; d < a.D; ++d) {
+    p.b_ih[d] = a.b_ih[d];
+    p.b_hh[d] = a.b_hh[d];
+    DS2_LAUNCH(f32_to_f16_kernel, 148 * 4, 256, 0, st, wn, a.w_hh[d], w16 + (size_t)d * wn);
+    int rc = make_tmap_f16(&p.tmW[d], w16 + (size_t)d * wn, 3, a.H, a.H, G, (size_t)a.H, (size_t)a.H * a.H, 64, UT, G);
+    if (rc) return rc;
+    rc = make_tmap_f16(&p.tmV[d], p.h16 + (size_t)d * a.T * a.B * a.H, 2, a.H, a.T * a.B, 1, (size_t)a.H, 0, 64, a.B, 1);
+    if (rc) return rc;
+  }
+  DS2_CHECK_CUDA(cudaMemsetAsync(ws, 0, 4096, st));
+  void* args[] = {&p};
+  DS2_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(THREADS), args, smem, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return DS2_OK;
+}
+
 template <int RNN>
 static int launch_fwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
   using namespace rp;
   const int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
+  if (!getenv("DS2_NO_RESIDENT")) {
+    int rc = launch_fwd_resident<RNN>(a, ws, ws_bytes, st);
+    if (rc != 1) return rc;
+  }
   PersistParams p{};
   p.T = a.T; p.B = a.B; p.NB = (a.B + 7) / 8 * 8; p.H = a.H; p.D = a.D; p.NT = a.H / UT; p.G = G;
   p.training = a.training;
@@ -376,8 +524,8 @@ static int launch_fwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t 
   set_acc_layout(p);
   p.err = static_cast<int*>(ws);
   p.bar = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + 128);
-  const size_t smem = fwd_smem_bytes(p.NB);
-  auto kern = rnn_fwd_persist_kernel<RNN>;
+  const size_t smem = one_cta_per_sm(fwd_smem_bytes(p.NB));
+  auto kern = rnn_fwd_persist_kernel<RNN, false>;
   static bool attr_done = false;
   static int max_blocks_per_sm = 0, num_sms = 0;
   if (!attr_done) {
@@ -459,6 +607,13 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // The CTA owns all 512 TMEM columns, so the allocation starts at address 0.  Using the literal keeps the
+  // accumulator operand of tcgen05.mma in a uniform register without the ELECT / R2UR.BROADCAST waterfall
+  // loop nvcc otherwise emits per MMA for a value it cannot prove warp-uniform.
+  if (tmem_base != 0 && threadIdx.x == 0) {
+    *(volatile int*)p.err = 2;
+    printf("ds2: unexpected TMEM base %u (block %d)\n", tmem_base, blockIdx.x);
+  }
   const uint32_t tx_bytes = (uint32_t)(UT * 128 + B * 128);
 
   if (warp == 0) {
@@ -504,10 +659,10 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
           if (c == NK - 1) trace_stamp(p.trace, step, 2);
           tc_fence_after();
           const uint64_t ad = a_base + (uint64_t)s * stage_step, bd = b_base + (uint64_t)s * stage_step;
-          mma_tf32(tmem_base, ad, bd, idesc, c > 0);
-          mma_tf32(tmem_base, ad + 2, bd + 2, idesc, 1);
-          mma_tf32(tmem_base, ad + 4, bd + 4, idesc, 1);
-          mma_tf32(tmem_base, ad + 6, bd + 6, idesc, 1);
+          mma_tf32(0u, ad, bd, idesc, c > 0);
+          mma_tf32(0u, ad + 2, bd + 2, idesc, 1);
+          mma_tf32(0u, ad + 4, bd + 4, idesc, 1);
+          mma_tf32(0u, ad + 6, bd + 6, idesc, 1);
           mma_commit(&empty[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -677,6 +832,13 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
   tc_fence_after();
   cluster_sync_all();                                     // peers' mbarriers are initialised
   const uint32_t tmem_base = *tmem_slot;
+  // The CTA owns all 512 TMEM columns, so the allocation starts at address 0.  Using the literal keeps the
+  // accumulator operand of tcgen05.mma in a uniform register without the ELECT / R2UR.BROADCAST waterfall
+  // loop nvcc otherwise emits per MMA for a value it cannot prove warp-uniform.
+  if (tmem_base != 0 && threadIdx.x == 0) {
+    *(volatile int*)p.err = 2;
+    printf("ds2: unexpected TMEM base %u (block %d)\n", tmem_base, blockIdx.x);
+  }
   const uint32_t tx_bytes = (uint32_t)(UM * 128 + B * 128);
 
   if (warp == 0) {
@@ -719,10 +881,10 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
           if (c == NK - 1) trace_stamp(p.trace, step, 2);
           tc_fence_after();
           const uint64_t ad = a_base + (uint64_t)s * stage_step, bd = b_base + (uint64_t)s * stage_step;
-          mma_tf32(tmem_base, ad, bd, idesc, c > 0);
-          mma_tf32(tmem_base, ad + 2, bd + 2, idesc, 1);
-          mma_tf32(tmem_base, ad + 4, bd + 4, idesc, 1);
-          mma_tf32(tmem_base, ad + 6, bd + 6, idesc, 1);
+          mma_tf32(0u, ad, bd, idesc, c > 0);
+          mma_tf32(0u, ad + 2, bd + 2, idesc, 1);
+          mma_tf32(0u, ad + 4, bd + 4, idesc, 1);
+          mma_tf32(0u, ad + 6, bd + 6, idesc, 1);
           mma_commit(&empty[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -841,7 +1003,7 @@ static int launch_bwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
   set_acc_layout(p);
   p.err = static_cast<int*>(ws);
   p.bar = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + 128);
-  const size_t smem = splitk_smem_bytes(p.NB);
+  const size_t smem = one_cta_per_sm(splitk_smem_bytes(p.NB));
   if (smem > 227 * 1024) return 1;
   auto kern = rnn_bwd_splitk_kernel<RNN>;
   static bool attr_done = false;
@@ -900,7 +1062,7 @@ static int launch_bwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t 
   set_acc_layout(p);
   p.err = static_cast<int*>(ws);
   p.bar = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + 128);
-  const size_t smem = fwd_smem_bytes(p.NB);
+  const size_t smem = one_cta_per_sm(fwd_smem_bytes(p.NB));
   auto kern = rnn_bwd_persist_kernel<RNN>;
   static bool attr_done = false;
   static int num_sms = 0;

@@ -154,5 +154,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 int make_tmap_2d(CUtensorMap* out, const float* base, int rows, int cols, int ld, int box_rows, int box_cols);
 int make_tmap_3d(CUtensorMap* out, const float* base, int d0, int d1, int d2, size_t stride1_floats,
                  size_t stride2_floats, int box0, int box1, int box2);
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, int d0, int d1, int d2, size_t stride1_elems,
+                  size_t stride2_elems, int box0, int box1, int box2);
 
 }  // namespace ds2

@@ -75,7 +75,7 @@ def input_sizes_from_percentages(input_percentages: torch.Tensor, t_max: int) ->
 def mask_time(x: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
     """reference model.py:59-68 — zero positions t >= length[b] on the last axis of (B,C,D,T)."""
     T = x.size(-1)
-    keep = (torch.arange(T)[None, :] < lengths.to(torch.int64)[:, None])  # (B,T)
+    keep = (torch.arange(T, device=x.device)[None, :] < lengths.to(device=x.device, dtype=torch.int64)[:, None])  # (B,T)
     return x * keep[:, None, None, :].to(x.dtype)
 
 

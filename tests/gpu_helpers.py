@@ -33,3 +33,11 @@ def rel(a, b):
 def oracle_cfg(rnn_type, bidirectional, H, layers, ctx=20):
     return O.OracleConfig(rnn_type=rnn_type, hidden_size=H, hidden_layers=layers, bidirectional=bidirectional,
                           lookahead_context=ctx)
+
+
+def rel_l2(a, b):
+    """||a-b||_2 / ||b||_2 — the noise-robust companion of `rel` for reduced-precision paths"""
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    d = float(b.norm())
+    return float((a - b).norm()) / (d if d > 0 else 1.0)
