@@ -37,7 +37,8 @@ T0 = time.time()
 
 
 def log(msg):
-    print(f"[bench +{time.time() - T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench +{time.time() - T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
 def host_cores():
@@ -295,8 +296,9 @@ def run_b200(args):
     prof = {}
     if rank == 0:
         lib.ds2_prof_enable(1)
-        for _ in range(2):
-            train_step(x_dev)
+    for _ in range(2):          # every rank runs the steps (they contain the all-reduce); rank 0 records ranges
+        train_step(x_dev)
+    if rank == 0:
         buf = (__import__("ctypes").c_char * 8192)()
         lib.ds2_prof_report(buf, 8192)
         lib.ds2_prof_enable(0)

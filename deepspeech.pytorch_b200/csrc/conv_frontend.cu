@@ -16,6 +16,8 @@
 // Backward: BN/Hardtanh/mask backward fused into two passes per BN (reduce, apply); conv2 data
 // gradient = two stride-1 convolutions (even / odd input rows) run through the SAME forward kernel
 // with re-packed (flipped, transposed) taps; weight gradients by dedicated reduction kernels.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ds2 {
@@ -422,8 +424,17 @@ static int launch_conv(const float* in, int B, int Cin, int Hin, int Win, const 
   return DS2_OK;
 }
 
+// tensor-core 32->32 convolution (conv_tc.cu)
+int conv_tc_run(const float* in_cl, int B, int T, int R_in, int R_out, const float* taps, int n_taps, int J,
+                int row_mul, int row_off, int row_step, int w_off, int w_step, float* out, size_t ob, size_t oc,
+                size_t orow, int out_row_mul, int out_row_off, const float* bias, const int32_t* out_len,
+                double* stat_sums, cudaStream_t st);
+int nchw_to_cl(int B, int R, int T, const float* in, float* out, cudaStream_t st);
+int pack_conv2_tc(const float* w2, float* wn_fwd, float* wd_bwd, cudaStream_t st);
+
 struct ConvWs {
   float *wpk1, *wpk2, *wTe, *wTo, *du2, *da1;
+  float *taps_f, *taps_b, *cl;     // tensor-core path: packed taps (21x352x32 each), channels-last staging
   double* sums;   // 4 x 64 doubles: fwd stats 1, fwd stats 2, bwd sums 2, bwd sums 1
 };
 static size_t conv_ws_carve(int B, int T, void* base, ConvWs* w) {
@@ -438,6 +449,9 @@ static size_t conv_ws_carve(int B, int T, void* base, ConvWs* w) {
   double* s = (double*)take(4 * 64 * sizeof(double)); if (w) w->sums = s;
   p = (float*)take((size_t)B * CO * DS2_CONV2_D * Tp * 4); if (w) w->du2 = p;
   p = (float*)take((size_t)B * CO * DS2_CONV1_D * Tp * 4); if (w) w->da1 = p;
+  p = (float*)take((size_t)21 * 352 * 32 * 4); if (w) w->taps_f = p;
+  p = (float*)take((size_t)21 * 352 * 32 * 4); if (w) w->taps_b = p;
+  p = (float*)take((size_t)B * CO * DS2_CONV1_D * Tp * 4); if (w) w->cl = p;
   return off;
 }
 
@@ -472,8 +486,18 @@ int ds2_conv_frontend_fwd(int B, int T, const float* x, const int32_t* out_len, 
   DS2_LAUNCH(bn2d_finalize_kernel, 1, 32, 0, st, (double)B * D1 * Tp, W.sums, g1, be1, rm1, rv1, training, momentum,
              eps, stats);
   DS2_LAUNCH(bn_act_kernel, 148 * 8, 256, 0, st, B, D1, Tp, z1, stats, g1, be1, out_len, a1);
-  rc = launch_conv<21, 11, 2, 1>(a1, B, CO, D1, Tp, W.wpk2, b2, z2, D2, Tp, (size_t)CO * D2 * Tp, (size_t)D2 * Tp,
-                                 (size_t)Tp, 10, 5, out_len, training ? W.sums + 64 : nullptr, st);
+  if (precision() == DS2_PREC_TF32 && !getenv("DS2_NO_CONV_TC")) {
+    // conv2 on tcgen05: channels-last copy of a1, packed taps, implicit GEMM with the kw taps folded into N
+    rc = nchw_to_cl(B, D1, Tp, a1, W.cl, st);
+    if (rc) return rc;
+    rc = pack_conv2_tc(w2, W.taps_f, nullptr, st);
+    if (rc) return rc;
+    rc = conv_tc_run(W.cl, B, Tp, D1, D2, W.taps_f, 21, 21, 2, -10, 1, 0, 1, z2, (size_t)CO * D2 * Tp, (size_t)D2 * Tp,
+                     (size_t)Tp, 1, 0, b2, out_len, training ? W.sums + 64 : nullptr, st);
+  } else {
+    rc = launch_conv<21, 11, 2, 1>(a1, B, CO, D1, Tp, W.wpk2, b2, z2, D2, Tp, (size_t)CO * D2 * Tp, (size_t)D2 * Tp,
+                                   (size_t)Tp, 10, 5, out_len, training ? W.sums + 64 : nullptr, st);
+  }
   if (rc) return rc;
   DS2_LAUNCH(bn2d_finalize_kernel, 1, 32, 0, st, (double)B * D2 * Tp, W.sums + 64, g2, be2, rm2, rv2, training,
              momentum, eps, stats + 64);
@@ -515,12 +539,27 @@ int ds2_conv_frontend_bwd(int B, int T, const float* x, const int32_t* out_len, 
   DS2_LAUNCH(pack_bwd_data_kernel, cdiv(CO * 10 * 11 * CO, 256), 256, 0, st, 1, w2, W.wTo);
   // even rows y=2j (41 rows), odd rows y=2j+1 (40 rows) of d(a1) (B,32,81,T')
   const size_t ob = (size_t)CO * D1 * Tp, oc = (size_t)D1 * Tp;
-  int rc = launch_conv<11, 11, 1, 1>(W.du2, B, CO, D2, Tp, W.wTe, nullptr, W.da1, 41, Tp, ob, oc, (size_t)2 * Tp, 5, 5,
-                                     nullptr, nullptr, st);
-  if (rc) return rc;
-  rc = launch_conv<10, 11, 1, 1>(W.du2, B, CO, D2, Tp, W.wTo, nullptr, W.da1 + Tp, 40, Tp, ob, oc, (size_t)2 * Tp, 4, 5,
-                                 nullptr, nullptr, st);
-  if (rc) return rc;
+  int rc;
+  if (precision() == DS2_PREC_TF32 && !getenv("DS2_NO_CONV_TC")) {
+    // data gradient on tcgen05: rows y=2i use taps kh=2m (d = i+5-m), rows y=2i+1 taps kh=2m+1
+    rc = nchw_to_cl(B, D2, Tp, W.du2, W.cl, st);
+    if (rc) return rc;
+    rc = pack_conv2_tc(w2, nullptr, W.taps_b, st);
+    if (rc) return rc;
+    rc = conv_tc_run(W.cl, B, Tp, D2, 41, W.taps_b, 21, 11, 1, 5, -1, 0, 2, W.da1, ob, oc, (size_t)Tp, 2, 0, nullptr,
+                     nullptr, nullptr, st);
+    if (rc) return rc;
+    rc = conv_tc_run(W.cl, B, Tp, D2, 40, W.taps_b, 21, 10, 1, 5, -1, 1, 2, W.da1, ob, oc, (size_t)Tp, 2, 1, nullptr,
+                     nullptr, nullptr, st);
+    if (rc) return rc;
+  } else {
+    rc = launch_conv<11, 11, 1, 1>(W.du2, B, CO, D2, Tp, W.wTe, nullptr, W.da1, 41, Tp, ob, oc, (size_t)2 * Tp, 5, 5,
+                                   nullptr, nullptr, st);
+    if (rc) return rc;
+    rc = launch_conv<10, 11, 1, 1>(W.du2, B, CO, D2, Tp, W.wTo, nullptr, W.da1 + Tp, 40, Tp, ob, oc, (size_t)2 * Tp, 4, 5,
+                                   nullptr, nullptr, st);
+    if (rc) return rc;
+  }
   // ---- stage 1: BN1 + Hardtanh + mask backward (natural layout, in place over da1)
   DS2_LAUNCH(bn_bwd_reduce_kernel<false>, dim3(cdiv(Tp, 32), cdiv(CO * D1, 32), B), dim3(32, 8), 0, st, B, D1, Tp,
              z1, stats, g1, be1, out_len, W.da1, W.da1, s1);

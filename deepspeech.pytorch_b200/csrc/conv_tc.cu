@@ -1,0 +1,270 @@
+// 32->32 channel convolution (conv2 forward and its data gradient) on tcgen05 tensor cores as an
+// im2col-free implicit GEMM with the horizontal taps folded into N ("tap-in-N"):
+//
+//   for an output row and one vertical tap j, with the input row r_j in channels-last layout (t, ci):
+//       D[p, (kw, co)] += sum_ci  X[r_j][p][ci] * Wn[j][(kw, co)][ci]          (M = 128 positions p,
+//                                                                               N = 11*32 = 352, K = 32)
+//   and after all vertical taps   out[t][co] = sum_kw D[t + kw - 5][(kw, co)]   (shifted sum, epilogue)
+//
+// The A tile of a tap is ONE contiguous TMA box (128 positions x 32 channels = 128-byte rows, 128B
+// swizzle, out-of-range rows / positions zero-filled by TMA = the convolution padding), the B tile is
+// the packed tap matrix (352 x 32); no descriptor tricks, no im2col buffer.  A tile produces 118
+// outputs (128 positions minus the 10-position halo).  Accumulators: 352 TMEM columns (two N=176 MMAs
+// per K=8 step).  Epilogue: per kw the 32-column block is read from TMEM and added into a shared-memory
+// output tile at row p-kw; then bias, length mask, NCHW store and the BatchNorm sum / sum-of-squares
+// partials of the forward pass.
+//
+// The data gradient of the stride-(2,1) convolution is the same kernel run twice (even / odd output
+// rows) with transposed, horizontally flipped taps (see pack kernels below).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace ds2 {
+namespace ctc_ns {}  // (no name clash with ctc.cu)
+
+namespace cv {
+constexpr int CH = 32, KW = 11, NN = KW * CH;      // 352
+constexpr int MP = 128, TO = MP - (KW - 1);         // positions per tile, outputs per tile (118)
+constexpr int A_BYTES = MP * 128;                   // 16 KB
+constexpr int W_HALF = (NN / 2) * 128;              // 176 rows x 128 B = 22528
+constexpr int STAGE_BYTES = A_BYTES + 2 * W_HALF;   // 61440
+constexpr int STAGES = 3;
+constexpr int OUT_LD = 33;
+constexpr int THREADS = 192;
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + (TO + 10) * OUT_LD * 4 + 256;
+}  // namespace cv
+
+struct ConvTcParams {
+  CUtensorMap tmA;   // 4-D (32 c, T, R_in, B) channels-last input
+  CUtensorMap tmW;   // 3-D (32 c, 352 n, taps) packed tap matrices
+  int B, T, R_in, R_out;
+  int J;                                   // vertical taps per output row
+  int row_mul, row_off, row_step;          // input row  = row_mul * d + row_off + j * row_step
+  int w_off, w_step;                       // tap matrix = w_off + j * w_step
+  float* out;                              // out[b*ob + c*oc + (out_row_mul*d + out_row_off)*orow + t]
+  size_t ob, oc, orow;
+  int out_row_mul, out_row_off;
+  const float* bias;                       // [32] or null
+  const int32_t* out_len;                  // [B] or null: positions t >= out_len[b] are written as 0
+  double* stat_sums;                       // [64] or null
+};
+
+__global__ void __launch_bounds__(cv::THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+  using namespace cv;
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* out_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);       // [TO+10][33]
+  uint64_t* full = reinterpret_cast<uint64_t*>(out_s + (TO + 10) * OUT_LD);   // 128*33 floats: 8-byte aligned
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum_bar = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int t0 = blockIdx.x * TO, d = blockIdx.y, b = blockIdx.z;
+
+  // vertical taps whose input row exists (the others contribute zeros: skip them)
+  int j_lo = 0, j_hi = p.J;
+  {
+    const int r0 = p.row_mul * d + p.row_off;
+    while (j_lo < j_hi && (r0 + j_lo * p.row_step < 0 || r0 + j_lo * p.row_step >= p.R_in)) ++j_lo;
+    while (j_hi > j_lo && (r0 + (j_hi - 1) * p.row_step < 0 || r0 + (j_hi - 1) * p.row_step >= p.R_in)) --j_hi;
+  }
+  const int nj = j_hi - j_lo;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmW);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < (TO + 10) * OUT_LD; i += THREADS) out_s[i] = 0.f;
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int jj = 0; jj < nj; ++jj) {
+        const int j = j_lo + jj;
+        const int r = p.row_mul * d + p.row_off + j * p.row_step;
+        const int wi = p.w_off + j * p.w_step;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], (uint32_t)STAGE_BYTES);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        // A: 128 positions starting at t0-5 (negative / beyond-T coordinates are zero-filled = padding)
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(smem_u32(st)), "l"(reinterpret_cast<uint64_t>(&p.tmA)), "r"(smem_u32(&full[s])), "r"(0),
+              "r"(t0 - 5), "r"(r), "r"(b)
+            : "memory");
+        tma_load_3d(st + A_BYTES, &p.tmW, &full[s], 0, 0, wi);
+        tma_load_3d(st + A_BYTES + W_HALF, &p.tmW, &full[s], 0, NN / 2, wi);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(FMT_TF32, MP, NN / 2);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int jj = 0; jj < nj; ++jj) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint64_t ad = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES));
+        const uint64_t b0 = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES));
+        const uint64_t b1 = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES + W_HALF));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          mma_tf32(tmem_base, ad + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), idesc, (jj | k) != 0);
+          mma_tf32(tmem_base + (uint32_t)(NN / 2), ad + (uint64_t)(2 * k), b1 + (uint64_t)(2 * k), idesc, (jj | k) != 0);
+        }
+        mma_commit(&empty[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      mma_commit(accum_bar);
+    }
+  } else {
+    const int q = warp % 4, e = threadIdx.x - 64;
+    const int pl = q * 32 + lane;                     // position inside the tile (TMEM lane)
+    if (nj > 0) {
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+      for (int kw = 0; kw < KW; ++kw) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kw * CH), v);
+        const int to = pl - kw;                       // output this position feeds through tap kw
+        if (to >= 0 && to < TO) {
+          float* row = out_s + to * OUT_LD;
+#pragma unroll
+          for (int c = 0; c < CH; ++c) row[c] += v[c];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    } else {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    // bias, mask, NCHW store: warp q owns channels 8q..8q+7, lanes run along time (128-byte stores);
+    // per-channel sum / sum of squares for the BatchNorm of the forward pass
+    const int L = p.out_len ? p.out_len[b] : p.T;
+    const int orow_idx = p.out_row_mul * d + p.out_row_off;
+    (void)e;
+    for (int cc = 0; cc < 8; ++cc) {
+      const int c = q * 8 + cc;
+      const float bv = p.bias ? p.bias[c] : 0.f;
+      float* op = p.out + (size_t)b * p.ob + (size_t)c * p.oc + (size_t)orow_idx * p.orow;
+      float s1 = 0.f, s2 = 0.f;
+      for (int to = lane; to < TO; to += 32) {
+        const int t = t0 + to;
+        if (t < p.T) {
+          const float val = (t < L) ? out_s[to * OUT_LD + c] + bv : 0.f;
+          op[t] = val;
+          s1 += val;
+          s2 = fmaf(val, val, s2);
+        }
+      }
+      if (p.stat_sums) {
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+          atomicAdd(&p.stat_sums[c], (double)s1);
+          atomicAdd(&p.stat_sums[CH + c], (double)s2);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---- packing ----------------------------------------------------------------------------------------
+// forward taps: Wn[kh][kw*32 + co][ci] = w2[co][ci][kh][kw]
+__global__ void pack_conv2_tc_fwd_kernel(const float* __restrict__ w2, float* __restrict__ wn) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x, n = 21 * cv::NN * 32;
+  if (i >= n) return;
+  int ci = i % 32, nn = (i / 32) % cv::NN, kh = i / (32 * cv::NN);
+  int kw = nn / 32, co = nn % 32;
+  wn[i] = w2[(((size_t)co * 32 + ci) * 21 + kh) * 11 + kw];
+}
+// data-gradient taps: Wd[kh][kwi*32 + ci][co] = w2[co][ci][kh][10 - kwi]   (K runs over co)
+__global__ void pack_conv2_tc_bwd_kernel(const float* __restrict__ w2, float* __restrict__ wd) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x, n = 21 * cv::NN * 32;
+  if (i >= n) return;
+  int co = i % 32, nn = (i / 32) % cv::NN, kh = i / (32 * cv::NN);
+  int kwi = nn / 32, ci = nn % 32;
+  wd[i] = w2[(((size_t)co * 32 + ci) * 21 + kh) * 11 + (10 - kwi)];
+}
+
+// NCHW (B,32,R,T) -> channels-last (B,R,T,32); grid (ceil(T/32), R, B), block (32, 8)
+__global__ void nchw_to_cl_kernel(int R, int T, const float* __restrict__ in, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, r = blockIdx.y, t0 = blockIdx.x * 32;
+  for (int c = threadIdx.y; c < 32; c += 8) {
+    int t = t0 + threadIdx.x;
+    tile[c][threadIdx.x] = (t < T) ? in[(((size_t)b * 32 + c) * R + r) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int t = t0 + j;
+    if (t < T) out[(((size_t)b * R + r) * T + t) * 32 + threadIdx.x] = tile[threadIdx.x][j];
+  }
+}
+
+int nchw_to_cl(int B, int R, int T, const float* in, float* out, cudaStream_t st) {
+  DS2_LAUNCH(nchw_to_cl_kernel, dim3(cdiv(T, 32), R, B), dim3(32, 8), 0, st, R, T, in, out);
+  return DS2_OK;
+}
+
+int pack_conv2_tc(const float* w2, float* wn_fwd, float* wd_bwd, cudaStream_t st) {
+  const int n = 21 * cv::NN * 32;
+  if (wn_fwd) DS2_LAUNCH(pack_conv2_tc_fwd_kernel, cdiv(n, 256), 256, 0, st, w2, wn_fwd);
+  if (wd_bwd) DS2_LAUNCH(pack_conv2_tc_bwd_kernel, cdiv(n, 256), 256, 0, st, w2, wd_bwd);
+  return DS2_OK;
+}
+
+// 4-D channels-last tensor map (32 c, T, R, B), box (32, 128, 1, 1)
+static int make_tmap_cl(CUtensorMap* out, const float* base, int T, int R, int B);
+
+// Runs the 32->32 tap-in-N convolution.  in_cl: (B, R_in, T, 32) channels-last; taps: (n_taps, 352, 32).
+int conv_tc_run(const float* in_cl, int B, int T, int R_in, int R_out, const float* taps, int n_taps, int J,
+                int row_mul, int row_off, int row_step, int w_off, int w_step, float* out, size_t ob, size_t oc,
+                size_t orow, int out_row_mul, int out_row_off, const float* bias, const int32_t* out_len,
+                double* stat_sums, cudaStream_t st) {
+  ConvTcParams p{};
+  int rc = make_tmap_cl(&p.tmA, in_cl, T, R_in, B);
+  if (rc) return rc;
+  rc = make_tmap_3d(&p.tmW, taps, 32, cv::NN, n_taps, 32, (size_t)32 * cv::NN, 32, cv::NN / 2, 1);
+  if (rc) return rc;
+  p.B = B; p.T = T; p.R_in = R_in; p.R_out = R_out; p.J = J;
+  p.row_mul = row_mul; p.row_off = row_off; p.row_step = row_step; p.w_off = w_off; p.w_step = w_step;
+  p.out = out; p.ob = ob; p.oc = oc; p.orow = orow; p.out_row_mul = out_row_mul; p.out_row_off = out_row_off;
+  p.bias = bias; p.out_len = out_len; p.stat_sums = stat_sums;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DS2_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cv::SMEM_BYTES));
+    attr_done = true;
+  }
+  dim3 grid(cdiv(T, cv::TO), R_out, B);
+  DS2_LAUNCH(conv_tc_kernel, grid, cv::THREADS, cv::SMEM_BYTES, st, p);
+  return DS2_OK;
+}
+
+}  // namespace ds2
+
+// tensor-map helper lives next to the other encoders (needs the driver entry point loaded in gemm_tc.cu)
+namespace ds2 {
+int make_tmap_4d_f32(CUtensorMap* out, const float* base, const unsigned long long dims[4],
+                     const unsigned long long strides_bytes[3], const unsigned int box[4]);
+static int make_tmap_cl(CUtensorMap* out, const float* base, int T, int R, int B) {
+  unsigned long long dims[4] = {32ull, (unsigned long long)T, (unsigned long long)R, (unsigned long long)B};
+  unsigned long long str[3] = {128ull, (unsigned long long)T * 128ull, (unsigned long long)R * T * 128ull};
+  unsigned int box[4] = {32u, (unsigned int)cv::MP, 1u, 1u};
+  return make_tmap_4d_f32(out, base, dims, str, box);
+}
+}  // namespace ds2

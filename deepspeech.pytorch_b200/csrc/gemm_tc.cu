@@ -77,6 +77,24 @@ int make_tmap_3d(CUtensorMap* out, const float* base, int d0, int d1, int d2, si
   return DS2_OK;
 }
 
+int make_tmap_4d_f32(CUtensorMap* out, const float* base, const unsigned long long dims[4],
+                     const unsigned long long strides_bytes[3], const unsigned int box[4]) {
+  int rc = load_encode();
+  if (rc) return rc;
+  cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gstr[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(out, g_tmap_dtype, 4, const_cast<float*>(base), gdim, gstr, bx, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d %llu,%llu,%llu,%llu) failed: %d", dims[0], dims[1], dims[2], dims[3], (int)r);
+    return DS2_ERR_CUDA;
+  }
+  return DS2_OK;
+}
+
 // fp16 tensor of rank 2 or 3 (d0 innermost), strides in ELEMENTS, 128B swizzle (box0 * 2 bytes <= 128)
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, int d0, int d1, int d2, size_t stride1,
                   size_t stride2, int box0, int box1, int box2) {

@@ -47,6 +47,8 @@ struct PersistParams {
   int T, B, NB, H, D, NT, G, training;
   const float* dy;      // bwd: (T,B,H)
   __half* h16;          // resident fwd: fp16 copy of hseq (D,T,B,H), the MMA operand of the next step
+  __half* dg16;         // resident bwd: scaled fp16 copy of dGh (T*B, D*G*H)
+  unsigned int* gmax;   // resident bwd: [D][T+1] float bits of max|dGh| per processed step (slot 0: bound from dY)
   long long* trace;     // optional: clock64 stamps of CTA 0, 4 per step
   const int32_t* len;
   float* gates;
@@ -424,7 +426,11 @@ static size_t fwd_smem_bytes(int NB) {
 
 size_t rnn_sweep_tc_workspace_bytes(int rnn, int T, int B, int H, int D) {
   const int G = rnn == DS2_RNN_LSTM ? 4 : (rnn == DS2_RNN_GRU ? 3 : 1);
-  return 4096 + align_up((size_t)D * G * H * H * 2, 256) + align_up((size_t)D * T * B * H * 2, 256) + 256;
+  const size_t fwd = 4096 + align_up((size_t)D * G * H * H * 2, 256) + align_up((size_t)D * T * B * H * 2, 256);
+  const size_t GH = (size_t)G * H;
+  const size_t bwd = 4096 + align_up((size_t)D * (T + 1) * 4, 256) + align_up((size_t)D * H * GH * 2, 256) +
+                     align_up((size_t)T * B * D * GH * 2, 256);
+  return (fwd > bwd ? fwd : bwd) + 256;
 }
 
 static void set_acc_layout(PersistParams& p) {
@@ -784,7 +790,23 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int RNN>
+// RES = true: the CTA's slice of W_hh^T (64 units x K/4, fp16, 128 KB at H=1024) is resident in shared memory and
+// the streamed operand is a SCALED fp16 copy of the gate gradients: dg16 = fp16(dGh * S_s), S_s a power of two
+// chosen from the maximum |dGh| of the previously processed step (global atomicMax, final at the grid barrier;
+// step 0 uses the bound max|dY|), so that the largest value sits near 2^8: 256x of fp16 headroom above, 2^-22 of
+// the maximum still representable below.  fp16 carries the same 10-bit mantissa as TF32.
+__device__ __forceinline__ __half to_half_sat(float v) {
+  return __float2half_rn(fminf(fmaxf(v, -65000.f), 65000.f));
+}
+__device__ __forceinline__ float pow2_scale_for(float m, float s_prev) {
+  if (!(m > 0.f)) return s_prev;
+  int ex;
+  frexpf(m, &ex);                       // m = f * 2^ex, f in [0.5, 1)
+  ex = max(-100, min(100, 8 - ex));
+  return ldexpf(1.f, ex);
+}
+
+template <int RNN, bool RES>
 __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __grid_constant__ PersistParams p) {
   using namespace rp;
   using namespace tc;
@@ -795,11 +817,14 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
   const int NB = p.NB, B = p.B, T = p.T, H = p.H, D = p.D;
   const int B_BYTES = NB * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   const int NBp = NB + 1;
-  float* part = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // [64][NBp] partial dh_rec of this CTA
+  const int NKR = (G * H / 4) / 64;                                      // resident: 64 fp16 of K per chunk
+  const int ring_bytes = RES ? NKR * STAGE_BYTES : STAGES * STAGE_BYTES;
+  float* part = reinterpret_cast<float*>(smem + ring_bytes);             // [64][NBp] partial dh_rec of this CTA
   float* cst = part + UM * NBp;                                          // [16][NBp] carried dc / dh
   int* lens_s = reinterpret_cast<int*>(cst + UT * NBp);
-  uint64_t* full = reinterpret_cast<uint64_t*>(lens_s + ((NB + 1) & ~1));
-  uint64_t* empty = full + STAGES;
+  unsigned int* cta_max = reinterpret_cast<unsigned int*>(lens_s + ((NB + 1) & ~1));   // [2] (8 bytes)
+  uint64_t* full = reinterpret_cast<uint64_t*>(cta_max + 2);             // resident: one per group of 4 chunks
+  uint64_t* empty = full + (RES ? 32 : STAGES);                          // resident: [0] = weights landed
   uint64_t* accum_bar = empty + STAGES;
   uint64_t* part_bar = accum_bar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(part_bar + 1);
@@ -819,10 +844,12 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmW[d]);
     tma_prefetch_desc(&p.tmV[d]);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < (RES ? 32 : STAGES); ++i) mbar_init(&full[i], 1);
+    for (int i = 0; i < STAGES; ++i) mbar_init(&empty[i], 1);
     mbar_init(accum_bar, 1);
     mbar_init(part_bar, 4);
     fence_barrier_init();
+    cta_max[0] = 0u;
   }
   for (int i = threadIdx.x; i < UT * NBp; i += THREADS) cst[i] = 0.f;
   for (int i = threadIdx.x; i < NB; i += THREADS) lens_s[i] = i < B ? p.len[i] : 0;
@@ -842,6 +869,27 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
   const uint32_t tx_bytes = (uint32_t)(UM * 128 + B * 128);
 
   if (warp == 0) {
+    if (RES) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&empty[0], (uint32_t)(NKR * UM * 128));
+        for (int c = 0; c < NKR; ++c) tma_load_2d(smem + c * A_BYTES, &p.tmW[d], &empty[0], kbase + c * 64, ut * UM);
+        uint8_t* vbuf = smem + NKR * A_BYTES;
+        for (int step = 1; step < T; ++step) {
+          const int t = d == 0 ? T - 1 - step : step;
+          const int tn = d == 0 ? t + 1 : t - 1;
+          grid_wait_counter(ctr, n_arrive * (unsigned int)step, p.err);
+          fence_proxy_async_all();
+          trace_stamp(p.trace, step, 0);
+          for (int g = 0; g * 4 < NKR; ++g) {
+            uint64_t* fb = full + g;
+            const int c0 = g * 4, c1 = min(NKR, c0 + 4);
+            mbar_arrive_expect_tx(fb, (uint32_t)((c1 - c0) * B * 128));
+            for (int c = c0; c < c1; ++c)
+              tma_load_2d(vbuf + c * B_BYTES, &p.tmV[d], fb, d * GH + kbase + c * 64, tn * B);
+          }
+        }
+      }
+    } else
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
@@ -867,6 +915,34 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
       }
     }
   } else if (warp == 1) {
+    if (RES) {
+      if (lane == 0) {
+        const uint32_t idesc = instr_desc(FMT_F16, MM, NB);
+        const uint64_t a_base = smem_desc_sw128(smem_u32(smem));
+        const uint64_t b_base = smem_desc_sw128(smem_u32(smem + NKR * A_BYTES));
+        const uint64_t a_step = (uint64_t)(A_BYTES >> 4), b_step = (uint64_t)(B_BYTES >> 4);
+        mbar_wait(&empty[0], 0);
+        uint32_t ph = 0;
+        for (int step = 1; step < T; ++step) {
+          for (int g = 0; g * 4 < NKR; ++g) {
+            mbar_wait(full + g, ph);
+            tc_fence_after();
+            if (g == 0) trace_stamp(p.trace, step, 1);
+            const int c0 = g * 4, c1 = min(NKR, c0 + 4);
+            if (c1 == NKR) trace_stamp(p.trace, step, 2);
+            for (int c = c0; c < c1; ++c) {
+              const uint64_t ad = a_base + (uint64_t)c * a_step, bd = b_base + (uint64_t)c * b_step;
+              mma_f16(0u, ad, bd, idesc, c > 0);
+              mma_f16(0u, ad + 2, bd + 2, idesc, 1);
+              mma_f16(0u, ad + 4, bd + 4, idesc, 1);
+              mma_f16(0u, ad + 6, bd + 6, idesc, 1);
+            }
+          }
+          mma_commit(accum_bar);
+          ph ^= 1;
+        }
+      }
+    } else
     if (lane == 0) {
       const uint32_t idesc = instr_desc(FMT_TF32, MM, NB);
       const uint64_t a_base = smem_desc_sw128(smem_u32(smem));
@@ -903,14 +979,24 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
       part_remote[r] = mapa_u32(part_local, (uint32_t)r);
       bar_remote[r] = mapa_u32(smem_u32(part_bar), (uint32_t)r);
     }
+    // resident: s_cur scales what this step writes, s_prev un-scales what this step's MMAs consumed
+    const unsigned int* gmax_d = RES ? p.gmax + (size_t)d * (T + 1) : nullptr;
+    float s_prev = 1.f, s_cur = 1.f;
+    if (RES) s_cur = pow2_scale_for(__uint_as_float(ld_acquire(gmax_d)), 1.f);
     for (int step = 0; step < T; ++step) {
       const int t = d == 0 ? T - 1 - step : step;
       const int tp = d == 0 ? t - 1 : t + 1;
       const bool tp_in = tp >= 0 && tp < T;
+      float lmax = 0.f;
       if (step > 0) {
         // publish this CTA's partial tile: row (16q + ul), 32 columns split over the two half-warps
         mbar_wait(accum_bar, acc_phase);
         tc_fence_after();
+        if (RES) {
+          // this step's MMAs ran, so the grid barrier was passed: every CTA's atomicMax of step-1 is final
+          s_prev = s_cur;
+          s_cur = pow2_scale_for(__uint_as_float(ld_acquire(gmax_d + step)), s_prev);
+        }
         if (e == 0) trace_stamp(p.trace, step, 3);
         for (int cb = 0; cb < NB; cb += 32) {
           float acc[32];
@@ -938,22 +1024,33 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
         const size_t si = (((size_t)d * T + t) * B + b) * H + u0 + ui;
         const size_t sp = (((size_t)d * T + (tp_in ? tp : 0)) * B + b) * H + u0 + ui;
         float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + ui;
+        __half* hp16 = RES ? p.dg16 + (((size_t)t * B + b) * D + d) * GH + u0 + ui : nullptr;
         if (!valid) {
 #pragma unroll
           for (int g = 0; g < G; ++g) gp[g * H] = 0.f;
           if (RNN == DS2_RNN_GRU) p.aux[si] = 0.f;
+          if (RES) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) hp16[g * H] = __float2half_rn(0.f);
+          }
         } else {
           float dh = p.dy[((size_t)t * B + b) * H + u0 + ui];
           if (step > 0) {
             const uint32_t off = (uint32_t)(((ks * UT + ui) * NBp + b) * 4);
-            dh += (ld_dsmem(part_remote[0] + off) + ld_dsmem(part_remote[1] + off)) +
-                  (ld_dsmem(part_remote[2] + off) + ld_dsmem(part_remote[3] + off));
+            const float rec = (ld_dsmem(part_remote[0] + off) + ld_dsmem(part_remote[1] + off)) +
+                              (ld_dsmem(part_remote[2] + off) + ld_dsmem(part_remote[3] + off));
+            dh += RES ? rec * (1.f / s_prev) : rec;
           }
           if (RNN == DS2_RNN_LSTM) {
             const float c_prev = pin ? p.aux[sp] : 0.f;
             LstmBwd r = lstm_cell_bwd(gp[0], gp[H], gp[2 * H], gp[3 * H], p.aux[si], c_prev, dh, cst[ui * NBp + b]);
             gp[0] = r.di; gp[H] = r.df; gp[2 * H] = r.dg; gp[3 * H] = r.d_o;
             cst[ui * NBp + b] = r.dc_prev;
+            if (RES) {
+              lmax = fmaxf(lmax, fmaxf(fmaxf(fabsf(r.di), fabsf(r.df)), fmaxf(fabsf(r.dg), fabsf(r.d_o))));
+              hp16[0] = to_half_sat(r.di * s_cur); hp16[H] = to_half_sat(r.df * s_cur);
+              hp16[2 * H] = to_half_sat(r.dg * s_cur); hp16[3 * H] = to_half_sat(r.d_o * s_cur);
+            }
           } else if (RNN == DS2_RNN_GRU) {
             const float h_prev = pin ? p.hseq[sp] : 0.f;
             dh += cst[ui * NBp + b];
@@ -961,14 +1058,30 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
             gp[0] = r.dr; gp[H] = r.dz; gp[2 * H] = r.dxn;
             p.aux[si] = r.dhn;
             cst[ui * NBp + b] = r.dh_prev;
+            if (RES) {
+              lmax = fmaxf(lmax, fmaxf(fabsf(r.dr), fmaxf(fabsf(r.dz), fabsf(r.dhn))));
+              hp16[0] = to_half_sat(r.dr * s_cur); hp16[H] = to_half_sat(r.dz * s_cur);
+              hp16[2 * H] = to_half_sat(r.dhn * s_cur);       // the h-side n-gate gradient (dGh_n)
+            }
           } else {
             const float h = p.hseq[si];
-            gp[0] = dh * (1.f - h * h);
+            const float dgv = dh * (1.f - h * h);
+            gp[0] = dgv;
+            if (RES) { lmax = fmaxf(lmax, fabsf(dgv)); hp16[0] = to_half_sat(dgv * s_cur); }
           }
         }
       }
+      if (RES) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        if (lane == 0) atomicMax(cta_max, __float_as_uint(lmax));     // non-negative floats order like uints
+      }
       named_bar_sync(1, 128);
       if (e == 0) {
+        if (RES) {
+          atomicMax(p.gmax + (size_t)d * (T + 1) + step + 1, cta_max[0]);
+          cta_max[0] = 0u;
+        }
         fence_proxy_async_all();
         red_release(ctr, 1u);
         trace_stamp(p.trace, step, 5);
@@ -984,8 +1097,98 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
 static size_t splitk_smem_bytes(int NB) {
   using namespace rp;
   size_t NBp = NB + 1;
-  return 1024 + (size_t)STAGES * (A_BYTES + (size_t)NB * 128) + ((64 + UT) * NBp + NB + 4) * sizeof(float) +
+  return 1024 + (size_t)STAGES * (A_BYTES + (size_t)NB * 128) + ((64 + UT) * NBp + NB + 8) * sizeof(float) +
          (2 * STAGES + 3) * sizeof(uint64_t) + 64;
+}
+
+// max |x| over n floats -> atomicMax on float bits (x >= 0 after fabs)
+__global__ void absmax_kernel(size_t n, const float* __restrict__ x, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (threadIdx.x % 32 == 0) atomicMax(out, __float_as_uint(m));
+}
+
+static size_t splitk_res_smem_bytes(int NB, int Kc) {
+  using namespace rp;
+  size_t NBp = NB + 1;
+  return 1024 + (size_t)(Kc / 64) * (A_BYTES + (size_t)NB * 128) + ((64 + UT) * NBp + NB + 8) * sizeof(float) +
+         (32 + STAGES + 3) * sizeof(uint64_t) + 64;
+}
+// workspace of the resident backward: [4 KB control][gmax D*(T+1) uints][W^T fp16: D*H*GH][dg16: T*B*D*GH]
+static size_t splitk_res_ws_bytes(int G, int T, int B, int H, int D) {
+  const size_t GH = (size_t)G * H;
+  return 4096 + align_up((size_t)D * (T + 1) * 4, 256) + align_up((size_t)D * H * GH * 2, 256) +
+         align_up((size_t)T * B * D * GH * 2, 256);
+}
+
+template <int RNN>
+static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
+  using namespace rp;
+  const int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
+  const int GH = G * a.H;
+  if (a.H % 64 != 0 || GH % 4 != 0 || (GH / 4) % 64 != 0 || (GH / 4) / 64 > 128) return 1;
+  if (ws_bytes < splitk_res_ws_bytes(G, a.T, a.B, a.H, a.D)) return 1;
+  PersistParams p{};
+  p.T = a.T; p.B = a.B; p.NB = (a.B + 7) / 8 * 8; p.H = a.H; p.D = a.D; p.NT = a.H / 64; p.G = G;
+  p.training = 1;
+  p.len = a.len; p.gates = a.gates; p.hseq = a.hseq; p.aux = a.aux; p.dy = a.dy;
+  p.trace = trace_ptr_from_env("DS2_TRACE_BWD");
+  set_acc_layout(p);
+  char* base = static_cast<char*>(ws);
+  p.err = reinterpret_cast<int*>(base);
+  p.bar = reinterpret_cast<unsigned int*>(base + 128);
+  size_t off = 4096;
+  p.gmax = reinterpret_cast<unsigned int*>(base + off); off += align_up((size_t)a.D * (a.T + 1) * 4, 256);
+  __half* wT16 = reinterpret_cast<__half*>(base + off); off += align_up((size_t)a.D * a.H * GH * 2, 256);
+  p.dg16 = reinterpret_cast<__half*>(base + off);
+  const size_t smem = one_cta_per_sm(splitk_res_smem_bytes(p.NB, GH / 4));
+  if (smem > 227 * 1024) return 1;
+  auto kern = rnn_bwd_splitk_kernel<RNN, true>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  const int grid = a.D * p.NT * 4;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = 4; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeCooperative;
+  attrs[1].val.cooperative = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 2;
+  int max_clusters = 0;
+  cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+  if (oe != cudaSuccess) { (void)cudaGetLastError(); return 1; }
+  if (max_clusters * 4 < grid) return 1;
+  DS2_CHECK_CUDA(cudaMemsetAsync(ws, 0, 4096 + align_up((size_t)a.D * (a.T + 1) * 4, 256), st));
+  const size_t wn = (size_t)a.H * GH;
+  for (int d = 0; d < a.D; ++d) {
+    DS2_LAUNCH(f32_to_f16_kernel, 148 * 4, 256, 0, st, wn, a.w_hh[d], wT16 + (size_t)d * wn);
+    int rc = make_tmap_f16(&p.tmW[d], wT16 + (size_t)d * wn, 2, GH, a.H, 1, (size_t)GH, 0, 64, 64, 1);
+    if (rc) return rc;
+    rc = make_tmap_f16(&p.tmV[d], p.dg16, 2, a.D * GH, a.T * a.B, 1, (size_t)a.D * GH, 0, 64, a.B, 1);
+    if (rc) return rc;
+    // step-0 scale: |dGh| <= |dh| = |dY[t_first]| for every cell type
+    const int t_first = d == 0 ? a.T - 1 : 0;
+    DS2_LAUNCH(absmax_kernel, 64, 256, 0, st, (size_t)a.B * a.H, a.dy + (size_t)t_first * a.B * a.H,
+               p.gmax + (size_t)d * (a.T + 1));
+  }
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
+  if (le != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 1;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return DS2_OK;
 }
 
 template <int RNN>
@@ -993,6 +1196,10 @@ static int launch_bwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
   using namespace rp;
   const int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
   const int GH = G * a.H;
+  if (!getenv("DS2_NO_RESIDENT")) {
+    int rc = launch_bwd_splitk_resident<RNN>(a, ws, ws_bytes, st);
+    if (rc != 1) return rc;
+  }
   if (a.H % 64 != 0 || (GH / 4) % BK != 0 || GH % 4 != 0) return 1;
   PersistParams p{};
   p.T = a.T; p.B = a.B; p.NB = (a.B + 7) / 8 * 8; p.H = a.H; p.D = a.D; p.NT = a.H / 64; p.G = G;
@@ -1005,7 +1212,7 @@ static int launch_bwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
   p.bar = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + 128);
   const size_t smem = one_cta_per_sm(splitk_smem_bytes(p.NB));
   if (smem > 227 * 1024) return 1;
-  auto kern = rnn_bwd_splitk_kernel<RNN>;
+  auto kern = rnn_bwd_splitk_kernel<RNN, false>;
   static bool attr_done = false;
   if (!attr_done) {
     DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
