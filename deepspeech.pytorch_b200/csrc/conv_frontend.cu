@@ -431,10 +431,12 @@ int conv_tc_run(const float* in_cl, int B, int T, int R_in, int R_out, const flo
                 double* stat_sums, cudaStream_t st);
 int nchw_to_cl(int B, int R, int T, const float* in, float* out, cudaStream_t st);
 int pack_conv2_tc(const float* w2, float* wn_fwd, float* wd_bwd, cudaStream_t st);
+int conv2_wgrad_tc(const float* dz2, const float* a1, float* a1_shifted, int B, int T, float* dw2, cudaStream_t st);
 
 struct ConvWs {
   float *wpk1, *wpk2, *wTe, *wTo, *du2, *da1;
   float *taps_f, *taps_b, *cl;     // tensor-core path: packed taps (21x352x32 each), channels-last staging
+  float* shifted;                  // tensor-core weight gradient: a1 shifted by 1,2,3 time steps
   double* sums;   // 4 x 64 doubles: fwd stats 1, fwd stats 2, bwd sums 2, bwd sums 1
 };
 static size_t conv_ws_carve(int B, int T, void* base, ConvWs* w) {
@@ -452,6 +454,7 @@ static size_t conv_ws_carve(int B, int T, void* base, ConvWs* w) {
   p = (float*)take((size_t)21 * 352 * 32 * 4); if (w) w->taps_f = p;
   p = (float*)take((size_t)21 * 352 * 32 * 4); if (w) w->taps_b = p;
   p = (float*)take((size_t)B * CO * DS2_CONV1_D * Tp * 4); if (w) w->cl = p;
+  p = (float*)take((size_t)3 * B * CO * DS2_CONV1_D * (Tp + 4) * 4); if (w) w->shifted = p;
   return off;
 }
 
@@ -486,7 +489,7 @@ int ds2_conv_frontend_fwd(int B, int T, const float* x, const int32_t* out_len, 
   DS2_LAUNCH(bn2d_finalize_kernel, 1, 32, 0, st, (double)B * D1 * Tp, W.sums, g1, be1, rm1, rv1, training, momentum,
              eps, stats);
   DS2_LAUNCH(bn_act_kernel, 148 * 8, 256, 0, st, B, D1, Tp, z1, stats, g1, be1, out_len, a1);
-  if (precision() == DS2_PREC_TF32 && !getenv("DS2_NO_CONV_TC")) {
+  if (precision() == DS2_PREC_TF32 && !getenv("DS2_NO_CONV_TC") && !getenv("DS2_NO_CONV_TC_FWD")) {
     // conv2 on tcgen05: channels-last copy of a1, packed taps, implicit GEMM with the kw taps folded into N
     rc = nchw_to_cl(B, D1, Tp, a1, W.cl, st);
     if (rc) return rc;
@@ -534,13 +537,20 @@ int ds2_conv_frontend_bwd(int B, int T, const float* x, const int32_t* out_len, 
   DS2_LAUNCH(bn_bwd_apply_kernel, dim3(cdiv(D2 * Tp, 256), CO, B), 256, 0, st, B, D2, Tp, 1.0 / ((double)B * D2 * Tp),
              z2, stats + 64, g2, out_len, s2, W.du2, db2);
   // ---- conv2 gradients
-  DS2_LAUNCH(conv2_dw_kernel, dim3(21, B), 256, 0, st, B, Tp, W.du2, a1, dw2);
+  {
+    int wrc = 1;
+    if (precision() == DS2_PREC_TF32 && !getenv("DS2_NO_CONV_TC") && !getenv("DS2_NO_CONV_TC_WGRAD")) {
+      wrc = conv2_wgrad_tc(W.du2, a1, W.shifted, B, Tp, dw2, st);
+      if (wrc < 0) return wrc;
+    }
+    if (wrc == 1) DS2_LAUNCH(conv2_dw_kernel, dim3(21, B), 256, 0, st, B, Tp, W.du2, a1, dw2);
+  }
   DS2_LAUNCH(pack_bwd_data_kernel, cdiv(CO * 11 * 11 * CO, 256), 256, 0, st, 0, w2, W.wTe);
   DS2_LAUNCH(pack_bwd_data_kernel, cdiv(CO * 10 * 11 * CO, 256), 256, 0, st, 1, w2, W.wTo);
   // even rows y=2j (41 rows), odd rows y=2j+1 (40 rows) of d(a1) (B,32,81,T')
   const size_t ob = (size_t)CO * D1 * Tp, oc = (size_t)D1 * Tp;
   int rc;
-  if (precision() == DS2_PREC_TF32 && !getenv("DS2_NO_CONV_TC")) {
+  if (precision() == DS2_PREC_TF32 && !getenv("DS2_NO_CONV_TC") && !getenv("DS2_NO_CONV_TC_DGRAD")) {
     // data gradient on tcgen05: rows y=2i use taps kh=2m (d = i+5-m), rows y=2i+1 taps kh=2m+1
     rc = nchw_to_cl(B, D2, Tp, W.du2, W.cl, st);
     if (rc) return rc;

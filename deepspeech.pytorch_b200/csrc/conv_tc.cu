@@ -20,7 +20,10 @@
 #include "tc_common.cuh"
 
 namespace ds2 {
-namespace ctc_ns {}  // (no name clash with ctc.cu)
+int make_tmap_4d_f32(CUtensorMap* out, const float* base, const unsigned long long dims[4],
+                     const unsigned long long strides_bytes[3], const unsigned int box[4]);
+int make_tmap_nd_f32(CUtensorMap* out, const float* base, int rank, const unsigned long long* dims,
+                     const unsigned long long* strides_bytes, const unsigned int* box);
 
 namespace cv {
 constexpr int CH = 32, KW = 11, NN = KW * CH;      // 352
@@ -252,6 +255,208 @@ int conv_tc_run(const float* in_cl, int B, int T, int R_in, int R_out, const flo
   }
   dim3 grid(cdiv(T, cv::TO), R_out, B);
   DS2_LAUNCH(conv_tc_kernel, grid, cv::THREADS, cv::SMEM_BYTES, st, p);
+  return DS2_OK;
+}
+
+// ---- weight gradient of conv2 on tensor cores ---------------------------------------------------------
+//   dW[co][ci][kh][kw] = sum_{b,d,t} dz2[b,co,d,t] * a1[b,ci,2d+kh-10,t+kw-5]
+// GEMM over time (K = t): A = dz2[b,:,d,t-chunk] (32 co rows, M padded to 64), B rows (kw,ci) =
+// a1[b,ci,r,t-chunk shifted by kw-5] (eleven 4 KB TMA boxes, N = 352), both operands K-major straight
+// out of the NCHW tensors.  A CTA owns one kh and a slice of the (b,d) pairs, accumulates all of them
+// in TMEM and finally adds its 32 x 352 tile into dW with fp32 atomics.
+namespace wg {
+constexpr int KT = 32;                               // time steps per K chunk (128 bytes)
+constexpr int A_BYTES = 64 * 128;                    // 64 M rows (32 valid)
+constexpr int B_BYTES = cv::NN * 128;                // 352 rows
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 53248
+constexpr int STAGES = 4;
+constexpr int THREADS = 192;
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256;
+}  // namespace wg
+
+struct WgradParams {
+  CUtensorMap tmDz;   // 4-D (T, 41, 32 co, B)
+  CUtensorMap tmA1;   // 4-D (T, 81, 32 ci, B)
+  CUtensorMap tmA1s;  // 5-D (T, 81, 32 ci, B, 3): copies of a1 shifted left by 1, 2, 3 time steps
+  int B, T, slices;
+  float* dw2;
+};
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(tc::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(tc::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3), "r"(c4)
+      : "memory");
+}
+
+// TMA needs 16-byte aligned box starts in the innermost dimension, so a shift by sh = kw-5 time steps is
+// split into a multiple of 4 (the box coordinate) and s = 0..3 (which pre-shifted copy is read):
+//   a1r[s-1][row][t'] = a1[row][t'-s]  for t' in [0, T+4)  (0 outside the row; rows padded to T+4 so that the
+//   shifted tail stays in bounds),  a1[t + sh] = a1r[s][t + sh + s]  with (sh + s) % 4 == 0.
+__global__ void shift_copies_kernel(size_t rows, int T, const float* __restrict__ a1, float* __restrict__ a1r) {
+  const int Tp = T + 4;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = rows * Tp, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const int t = (int)(i % Tp);
+    const float* src = a1 + (i / Tp) * T;
+#pragma unroll
+    for (int sft = 1; sft <= 3; ++sft) {
+      const int ts = t - sft;
+      a1r[(size_t)(sft - 1) * n + i] = (ts >= 0 && ts < T) ? src[ts] : 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(wg::THREADS, 1) conv2_wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
+  using namespace wg;
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum_bar = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int kh = blockIdx.x, slice = blockIdx.y;
+  const int pairs = p.B * DS2_CONV2_D;
+  const int per = (pairs + p.slices - 1) / p.slices;
+  const int p0 = slice * per, p1 = min(pairs, p0 + per);
+  const int nkt = (p.T + KT - 1) / KT;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmDz);
+    tma_prefetch_desc(&p.tmA1);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // number of K chunks this CTA will issue (rows outside the input are skipped)
+  int nchunks = 0;
+  for (int pi = p0; pi < p1; ++pi) {
+    const int d = pi % DS2_CONV2_D, r = 2 * d + kh - 10;
+    if (r >= 0 && r < DS2_CONV1_D) nchunks += nkt;
+  }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int pi = p0; pi < p1; ++pi) {
+        const int b = pi / DS2_CONV2_D, d = pi % DS2_CONV2_D, r = 2 * d + kh - 10;
+        if (r < 0 || r >= DS2_CONV1_D) continue;
+        for (int kt = 0; kt < nkt; ++kt) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], (uint32_t)(32 * 128 + cv::NN * 128));
+          uint8_t* st = smem + s * STAGE_BYTES;
+          tma_load_4d(st, &p.tmDz, &full[s], kt * KT, d, 0, b);
+#pragma unroll 1
+          for (int kw = 0; kw < cv::KW; ++kw) {
+            const int sh = kw - 5, sft = (4 - (((sh % 4) + 4) % 4)) % 4;      // (sh + sft) % 4 == 0
+            if (sft == 0) tma_load_4d(st + A_BYTES + kw * 32 * 128, &p.tmA1, &full[s], kt * KT + sh, r, 0, b);
+            else tma_load_5d(st + A_BYTES + kw * 32 * 128, &p.tmA1s, &full[s], kt * KT + sh + sft, r, 0, b, sft - 1);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(FMT_TF32, 64, cv::NN / 2);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint64_t ad = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES));
+        const uint64_t b0 = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES));
+        const uint64_t b1 = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES + cv::W_HALF));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          mma_tf32(tmem_base, ad + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), idesc, (c | k) != 0);
+          mma_tf32(tmem_base + (uint32_t)(cv::NN / 2), ad + (uint64_t)(2 * k), b1 + (uint64_t)(2 * k), idesc, (c | k) != 0);
+        }
+        mma_commit(&empty[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      mma_commit(accum_bar);
+    }
+  } else if (nchunks > 0) {
+    // M = 64 accumulator layout: row m lives in TMEM lane (m % 16) + 32 * (m / 16); valid rows: co = 0..31
+    const int q = warp % 4;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    if (q < 2) {
+      const int co = q * 16 + lane;
+      for (int kw = 0; kw < cv::KW; ++kw) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kw * 32), v);
+        if (lane < 16) {
+#pragma unroll
+          for (int ci = 0; ci < 32; ++ci)
+            atomicAdd(&p.dw2[(((size_t)co * 32 + ci) * 21 + kh) * 11 + kw], v[ci]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// dz2: (B,32,41,T) NCHW gate... conv2 output gradient; a1: (B,32,81,T) NCHW; dw2 (32,32,21,11) must be zeroed.
+// Returns 1 when the shape is not eligible (row pitch T*4 bytes must be a multiple of 16).
+int conv2_wgrad_tc(const float* dz2, const float* a1, float* a1_shifted /* 3*B*32*81*(T+4) floats */, int B, int T,
+                   float* dw2, cudaStream_t st) {
+  if (T % 4 != 0) return 1;
+  WgradParams p{};
+  {
+    const size_t rows = (size_t)B * 32 * 81;
+    DS2_LAUNCH(shift_copies_kernel, 148 * 8, 256, 0, st, rows, T, a1, a1_shifted);
+    const unsigned long long Tq = (unsigned long long)T + 4;
+    unsigned long long dims[5] = {Tq, 81ull, 32ull, (unsigned long long)B, 3ull};
+    unsigned long long str[4] = {Tq * 4, 81ull * Tq * 4, 32ull * 81 * Tq * 4, (unsigned long long)rows * Tq * 4};
+    unsigned int box[5] = {32u, 1u, 32u, 1u, 1u};
+    int rc = make_tmap_nd_f32(&p.tmA1s, a1_shifted, 5, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    unsigned long long dims[4] = {(unsigned long long)T, 41ull, 32ull, (unsigned long long)B};
+    unsigned long long str[3] = {(unsigned long long)T * 4, (unsigned long long)41 * T * 4, (unsigned long long)32 * 41 * T * 4};
+    unsigned int box[4] = {32u, 1u, 32u, 1u};
+    int rc = make_tmap_4d_f32(&p.tmDz, dz2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    unsigned long long dims[4] = {(unsigned long long)T, 81ull, 32ull, (unsigned long long)B};
+    unsigned long long str[3] = {(unsigned long long)T * 4, (unsigned long long)81 * T * 4, (unsigned long long)32 * 81 * T * 4};
+    unsigned int box[4] = {32u, 1u, 32u, 1u};
+    int rc = make_tmap_4d_f32(&p.tmA1, a1, dims, str, box);
+    if (rc) return rc;
+  }
+  p.B = B; p.T = T; p.slices = 7; p.dw2 = dw2;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DS2_CHECK_CUDA(cudaFuncSetAttribute(conv2_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
+    attr_done = true;
+  }
+  DS2_LAUNCH(conv2_wgrad_tc_kernel, dim3(21, p.slices), wg::THREADS, wg::SMEM_BYTES, st, p);
   return DS2_OK;
 }
 

@@ -77,6 +77,24 @@ int make_tmap_3d(CUtensorMap* out, const float* base, int d0, int d1, int d2, si
   return DS2_OK;
 }
 
+int make_tmap_nd_f32(CUtensorMap* out, const float* base, int rank, const unsigned long long* dims,
+                     const unsigned long long* strides_bytes, const unsigned int* box) {
+  int rc = load_encode();
+  if (rc) return rc;
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = g_encode(out, g_tmap_dtype, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr, bx, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(rank %d) failed: %d", rank, (int)r);
+    return DS2_ERR_CUDA;
+  }
+  return DS2_OK;
+}
+
 int make_tmap_4d_f32(CUtensorMap* out, const float* base, const unsigned long long dims[4],
                      const unsigned long long strides_bytes[3], const unsigned int box[4]) {
   int rc = load_encode();

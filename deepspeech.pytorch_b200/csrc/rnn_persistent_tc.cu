@@ -988,6 +988,35 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
       const int tp = d == 0 ? t - 1 : t + 1;
       const bool tp_in = tp >= 0 && tp < T;
       float lmax = 0.f;
+      // Saved activations / states / dY of this step do not depend on the recurrence: fetch them into
+      // registers BEFORE waiting for the MMAs so their latency hides behind the tensor-core phase.
+      constexpr int NPF = 4;                              // (unit, batch) pairs per thread that are prefetched
+      const bool prefetch = UT * B <= 128 * NPF;
+      float pg[NPF][4], pa[NPF], pb[NPF], pdy[NPF];
+      if (prefetch) {
+#pragma unroll
+        for (int j = 0; j < NPF; ++j) {
+          const int pi = e + 128 * j;
+          pa[j] = pb[j] = pdy[j] = 0.f;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) pg[j][g] = 0.f;
+          if (pi < UT * B) {
+            const int ui = pi % UT, b = pi / UT;
+            if (t < lens_s[b]) {
+              const bool pin = tp_in && (d == 0 || tp < lens_s[b]);
+              const size_t si = (((size_t)d * T + t) * B + b) * H + u0 + ui;
+              const size_t sp = (((size_t)d * T + (tp_in ? tp : 0)) * B + b) * H + u0 + ui;
+              const float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + ui;
+#pragma unroll
+              for (int g = 0; g < G; ++g) pg[j][g] = gp[g * H];
+              pdy[j] = p.dy[((size_t)t * B + b) * H + u0 + ui];
+              if (RNN == DS2_RNN_LSTM) { pa[j] = p.aux[si]; pb[j] = pin ? p.aux[sp] : 0.f; }
+              else if (RNN == DS2_RNN_GRU) { pa[j] = p.aux[si]; pb[j] = pin ? p.hseq[sp] : 0.f; }
+              else pa[j] = p.hseq[si];
+            }
+          }
+        }
+      }
       if (step > 0) {
         // publish this CTA's partial tile: row (16q + ul), 32 columns split over the two half-warps
         mbar_wait(accum_bar, acc_phase);
@@ -1017,12 +1046,12 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
         part_phase ^= 1;
       }
       if (e == 0) trace_stamp(p.trace, step, 4);
-      for (int pi = e; pi < UT * B; pi += 128) {
+      const float inv_prev = 1.f / s_prev;
+      // one (unit, batch) pair: recurrent term from the four partial tiles, gate backward, stores
+      auto finish_pair = [&](int pi, float g0, float g1, float g2, float g3, float a_si, float a_prev, float dyv) {
         const int ui = pi % UT, b = pi / UT;
         const bool valid = t < lens_s[b];
-        const bool pin = tp_in && (d == 0 || tp < lens_s[b]);
         const size_t si = (((size_t)d * T + t) * B + b) * H + u0 + ui;
-        const size_t sp = (((size_t)d * T + (tp_in ? tp : 0)) * B + b) * H + u0 + ui;
         float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + ui;
         __half* hp16 = RES ? p.dg16 + (((size_t)t * B + b) * D + d) * GH + u0 + ui : nullptr;
         if (!valid) {
@@ -1033,42 +1062,64 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
 #pragma unroll
             for (int g = 0; g < G; ++g) hp16[g * H] = __float2half_rn(0.f);
           }
+          return;
+        }
+        float dh = dyv;
+        if (step > 0) {
+          const uint32_t off = (uint32_t)(((ks * UT + ui) * NBp + b) * 4);
+          const float rec = (ld_dsmem(part_remote[0] + off) + ld_dsmem(part_remote[1] + off)) +
+                            (ld_dsmem(part_remote[2] + off) + ld_dsmem(part_remote[3] + off));
+          dh += RES ? rec * inv_prev : rec;
+        }
+        if (RNN == DS2_RNN_LSTM) {
+          LstmBwd r = lstm_cell_bwd(g0, g1, g2, g3, a_si, a_prev, dh, cst[ui * NBp + b]);
+          gp[0] = r.di; gp[H] = r.df; gp[2 * H] = r.dg; gp[3 * H] = r.d_o;
+          cst[ui * NBp + b] = r.dc_prev;
+          if (RES) {
+            lmax = fmaxf(lmax, fmaxf(fmaxf(fabsf(r.di), fabsf(r.df)), fmaxf(fabsf(r.dg), fabsf(r.d_o))));
+            hp16[0] = to_half_sat(r.di * s_cur); hp16[H] = to_half_sat(r.df * s_cur);
+            hp16[2 * H] = to_half_sat(r.dg * s_cur); hp16[3 * H] = to_half_sat(r.d_o * s_cur);
+          }
+        } else if (RNN == DS2_RNN_GRU) {
+          dh += cst[ui * NBp + b];
+          GruBwd r = gru_cell_bwd(g0, g1, g2, a_si, a_prev, dh);
+          gp[0] = r.dr; gp[H] = r.dz; gp[2 * H] = r.dxn;
+          p.aux[si] = r.dhn;
+          cst[ui * NBp + b] = r.dh_prev;
+          if (RES) {
+            lmax = fmaxf(lmax, fmaxf(fabsf(r.dr), fmaxf(fabsf(r.dz), fabsf(r.dhn))));
+            hp16[0] = to_half_sat(r.dr * s_cur); hp16[H] = to_half_sat(r.dz * s_cur);
+            hp16[2 * H] = to_half_sat(r.dhn * s_cur);       // the h-side n-gate gradient (dGh_n)
+          }
         } else {
-          float dh = p.dy[((size_t)t * B + b) * H + u0 + ui];
-          if (step > 0) {
-            const uint32_t off = (uint32_t)(((ks * UT + ui) * NBp + b) * 4);
-            const float rec = (ld_dsmem(part_remote[0] + off) + ld_dsmem(part_remote[1] + off)) +
-                              (ld_dsmem(part_remote[2] + off) + ld_dsmem(part_remote[3] + off));
-            dh += RES ? rec * (1.f / s_prev) : rec;
+          const float dgv = dh * (1.f - a_si * a_si);
+          gp[0] = dgv;
+          if (RES) { lmax = fmaxf(lmax, fabsf(dgv)); hp16[0] = to_half_sat(dgv * s_cur); }
+        }
+      };
+      if (prefetch) {
+#pragma unroll
+        for (int j = 0; j < NPF; ++j) {
+          const int pi = e + 128 * j;
+          if (pi < UT * B) finish_pair(pi, pg[j][0], pg[j][1], pg[j][2], pg[j][3], pa[j], pb[j], pdy[j]);
+        }
+      } else {
+        for (int pi = e; pi < UT * B; pi += 128) {
+          const int ui = pi % UT, b = pi / UT;
+          float g4[4] = {0.f, 0.f, 0.f, 0.f}, a_si = 0.f, a_prev = 0.f, dyv = 0.f;
+          if (t < lens_s[b]) {
+            const bool pin = tp_in && (d == 0 || tp < lens_s[b]);
+            const size_t si = (((size_t)d * T + t) * B + b) * H + u0 + ui;
+            const size_t sp = (((size_t)d * T + (tp_in ? tp : 0)) * B + b) * H + u0 + ui;
+            const float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + ui;
+#pragma unroll
+            for (int g = 0; g < G; ++g) g4[g] = gp[g * H];
+            dyv = p.dy[((size_t)t * B + b) * H + u0 + ui];
+            if (RNN == DS2_RNN_LSTM) { a_si = p.aux[si]; a_prev = pin ? p.aux[sp] : 0.f; }
+            else if (RNN == DS2_RNN_GRU) { a_si = p.aux[si]; a_prev = pin ? p.hseq[sp] : 0.f; }
+            else a_si = p.hseq[si];
           }
-          if (RNN == DS2_RNN_LSTM) {
-            const float c_prev = pin ? p.aux[sp] : 0.f;
-            LstmBwd r = lstm_cell_bwd(gp[0], gp[H], gp[2 * H], gp[3 * H], p.aux[si], c_prev, dh, cst[ui * NBp + b]);
-            gp[0] = r.di; gp[H] = r.df; gp[2 * H] = r.dg; gp[3 * H] = r.d_o;
-            cst[ui * NBp + b] = r.dc_prev;
-            if (RES) {
-              lmax = fmaxf(lmax, fmaxf(fmaxf(fabsf(r.di), fabsf(r.df)), fmaxf(fabsf(r.dg), fabsf(r.d_o))));
-              hp16[0] = to_half_sat(r.di * s_cur); hp16[H] = to_half_sat(r.df * s_cur);
-              hp16[2 * H] = to_half_sat(r.dg * s_cur); hp16[3 * H] = to_half_sat(r.d_o * s_cur);
-            }
-          } else if (RNN == DS2_RNN_GRU) {
-            const float h_prev = pin ? p.hseq[sp] : 0.f;
-            dh += cst[ui * NBp + b];
-            GruBwd r = gru_cell_bwd(gp[0], gp[H], gp[2 * H], p.aux[si], h_prev, dh);
-            gp[0] = r.dr; gp[H] = r.dz; gp[2 * H] = r.dxn;
-            p.aux[si] = r.dhn;
-            cst[ui * NBp + b] = r.dh_prev;
-            if (RES) {
-              lmax = fmaxf(lmax, fmaxf(fabsf(r.dr), fmaxf(fabsf(r.dz), fabsf(r.dhn))));
-              hp16[0] = to_half_sat(r.dr * s_cur); hp16[H] = to_half_sat(r.dz * s_cur);
-              hp16[2 * H] = to_half_sat(r.dhn * s_cur);       // the h-side n-gate gradient (dGh_n)
-            }
-          } else {
-            const float h = p.hseq[si];
-            const float dgv = dh * (1.f - h * h);
-            gp[0] = dgv;
-            if (RES) { lmax = fmaxf(lmax, fabsf(dgv)); hp16[0] = to_half_sat(dgv * s_cur); }
-          }
+          finish_pair(pi, g4[0], g4[1], g4[2], g4[3], a_si, a_prev, dyv);
         }
       }
       if (RES) {
