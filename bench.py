@@ -220,6 +220,9 @@ def run_b200(args):
     from deepspeech_pytorch_b200.optim import FlatParams, FusedOptimizer
     from oracle import ds2_oracle as O   # synthetic batch generator + cpu_baseline leg only
 
+    # NCCL prints its version banner on stdout: keep fd 1 clean for the single JSON line
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = D.init_from_env()
     assert torch.cuda.is_available(), "bench.py (impl b200) needs a GPU; there is no CPU fallback"
     torch.cuda.set_device(local)
@@ -358,7 +361,10 @@ def run_b200(args):
             line["stock_cuda_baseline"] = stock_cuda_baseline(args.workload)
         except Exception as e:  # pragma: no cover
             line["stock_cuda_baseline"] = {"error": repr(e)}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         torch.distributed.destroy_process_group()
 

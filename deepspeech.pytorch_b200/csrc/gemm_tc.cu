@@ -141,9 +141,24 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*b
 constexpr int THREADS = 192;
 }  // namespace gtc
 
+// MN-major operand tile (the matrix is stored (K, MN) row-major, i.e. "transposed" for this GEMM): the tile is
+// loaded as ROWS/32 TMA boxes of (32 mn x 32 k): box i occupies 4 KB = 32 k-rows of 128 bytes, 8-row groups are
+// 1024 B apart (stride byte offset), consecutive 32-wide MN atoms are 4096 B apart (leading byte offset); an
+// MMA (K = 8) consumes one 8-row group, so the k-step advance is 1024 B.  No transpose pass is needed.
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(gtc::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-               float alpha, float beta, float* __restrict__ C, int ldc) {
+               float alpha, float beta, float* __restrict__ C, int ldc, int swap_lbo_sbo) {
   using namespace gtc;
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
@@ -176,23 +191,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-        tma_load_2d(smem + s * STAGE_BYTES, &tmA, &full[s], kb * BK, m0);
-        tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &tmB, &full[s], kb * BK, n0);
+        if (A_MN) {
+#pragma unroll
+          for (int i = 0; i < BM / 32; ++i)
+            tma_load_2d(smem + s * STAGE_BYTES + i * 4096, &tmA, &full[s], m0 + i * 32, kb * BK);
+        } else {
+          tma_load_2d(smem + s * STAGE_BYTES, &tmA, &full[s], kb * BK, m0);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int i = 0; i < BN / 32; ++i)
+            tma_load_2d(smem + s * STAGE_BYTES + A_BYTES + i * 4096, &tmB, &full[s], n0 + i * 32, kb * BK);
+        } else {
+          tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &tmB, &full[s], kb * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = instr_desc(FMT_TF32, BM, BN);
+      constexpr uint32_t idesc = instr_desc(FMT_TF32, BM, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+      const uint32_t lbo = swap_lbo_sbo ? 1024u : 4096u, sbo = swap_lbo_sbo ? 4096u : 1024u;
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint64_t adesc = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES));
-        const uint64_t bdesc = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES));
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES), b_addr = smem_u32(smem + s * STAGE_BYTES + A_BYTES);
+        const uint64_t adesc = A_MN ? smem_desc_sw128_mn(a_addr, lbo, sbo) : smem_desc_sw128(a_addr);
+        const uint64_t bdesc = B_MN ? smem_desc_sw128_mn(b_addr, lbo, sbo) : smem_desc_sw128(b_addr);
+        // k-step: K-major +32 B inside the 128B swizzle row; MN-major +1024 B (the next group of 8 k-rows)
+        constexpr uint64_t a_adv = A_MN ? 64 : 2, b_adv = B_MN ? 64 : 2;
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k)   // advance 32 bytes (8 tf32) inside the 128B swizzle row
-          mma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        for (int k = 0; k < BK / 8; ++k)
+          mma_tf32(tmem_base, adesc + (uint64_t)k * a_adv, bdesc + (uint64_t)k * b_adv, idesc, (kb | k) != 0);
         mma_commit(&empty[s]);             // stage reusable when these MMAs have read it
       }
       mma_commit(accum_bar);               // accumulator complete
@@ -262,6 +293,9 @@ int transpose(int R, int C, const float* in, float* out, cudaStream_t st) {
 
 static inline size_t k4(int K) { return (size_t)((K + 3) / 4 * 4); }
 
+// MN-major operands are read in place (DS2_GEMM_TRANSPOSE=1 restores the transposing path for comparison)
+static bool use_mn_major() { static int v = -1; if (v < 0) v = getenv("DS2_GEMM_TRANSPOSE") ? 0 : 1; return v == 1; }
+
 size_t gemm_tc_workspace_bytes(int transA, int transB, int M, int N, int K) {
   size_t n = 0;
   if (transA) n += align_up((size_t)M * k4(K) * 4, 256);
@@ -271,45 +305,67 @@ size_t gemm_tc_workspace_bytes(int transA, int transB, int M, int N, int K) {
 
 static bool tc_eligible(int M, int N, int K) { return K >= 32 && M >= 32 && N >= 16 && (long long)M * N * K >= (1 << 18); }
 
+template <bool A_MN, bool B_MN>
+static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, float alpha, float beta,
+                          float* C, int ldc, cudaStream_t st) {
+  auto kern = gemm_tc_kernel<A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gtc::SMEM_BYTES));
+    attr_set = true;
+  }
+  static int swap = -1;
+  if (swap < 0) swap = getenv("DS2_GEMM_SWAP_LBO_SBO") ? 1 : 0;
+  dim3 grid(cdiv(N, gtc::BN), cdiv(M, gtc::BM));
+  DS2_LAUNCH(kern, grid, gtc::THREADS, gtc::SMEM_BYTES, st, tmA, tmB, M, N, K, alpha, beta, C, ldc, swap);
+  return DS2_OK;
+}
+
 int gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
             int ldb, float beta, float* C, int ldc, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (!tc_eligible(M, N, K)) return 1;
   Arena ar(ws, ws_bytes);
   const float* Ak = A;
   int ldak = lda;
-  if (transA) {  // stored (K, M) -> (M, K)
-    float* t = ar.take<float>((size_t)M * k4(K));
-    if (!t) return 1;
-    int rc = transpose_strided(K, M, A, (size_t)lda, t, k4(K), st);
-    if (rc) return rc;
-    Ak = t;
-    ldak = (int)k4(K);
+  bool a_mn = false, b_mn = false;
+  if (transA) {  // stored (K, M)
+    if (use_mn_major() && (lda & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0) {
+      a_mn = true;
+    } else {
+      float* t = ar.take<float>((size_t)M * k4(K));
+      if (!t) return 1;
+      int rc = transpose_strided(K, M, A, (size_t)lda, t, k4(K), st);
+      if (rc) return rc;
+      Ak = t;
+      ldak = (int)k4(K);
+    }
   }
   const float* Bk = B;
   int ldbk = ldb;
-  if (!transB) {  // stored (K, N) -> (N, K)
-    float* t = ar.take<float>((size_t)N * k4(K));
-    if (!t) return 1;
-    int rc = transpose_strided(K, N, B, (size_t)ldb, t, k4(K), st);
-    if (rc) return rc;
-    Bk = t;
-    ldbk = (int)k4(K);
+  if (!transB) {  // stored (K, N)
+    if (use_mn_major() && (ldb & 3) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0) {
+      b_mn = true;
+    } else {
+      float* t = ar.take<float>((size_t)N * k4(K));
+      if (!t) return 1;
+      int rc = transpose_strided(K, N, B, (size_t)ldb, t, k4(K), st);
+      if (rc) return rc;
+      Bk = t;
+      ldbk = (int)k4(K);
+    }
   }
   if ((ldak & 3) || (ldbk & 3) || (reinterpret_cast<uintptr_t>(Ak) & 15) || (reinterpret_cast<uintptr_t>(Bk) & 15))
     return 1;
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_2d(&tmA, Ak, M, K, ldak, gtc::BM, gtc::BK);
+  // K-major: matrix [rows, K] box (32 k, rows) ; MN-major: matrix [K, rows] box (32 rows, 32 k)
+  int rc = a_mn ? make_tmap_2d(&tmA, Ak, K, M, ldak, 32, 32) : make_tmap_2d(&tmA, Ak, M, K, ldak, gtc::BM, gtc::BK);
   if (rc) return rc;
-  rc = make_tmap_2d(&tmB, Bk, N, K, ldbk, gtc::BN, gtc::BK);
+  rc = b_mn ? make_tmap_2d(&tmB, Bk, K, N, ldbk, 32, 32) : make_tmap_2d(&tmB, Bk, N, K, ldbk, gtc::BN, gtc::BK);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DS2_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gtc::SMEM_BYTES));
-    attr_set = true;
-  }
-  dim3 grid(cdiv(N, gtc::BN), cdiv(M, gtc::BM));
-  DS2_LAUNCH(gemm_tc_kernel, grid, gtc::THREADS, gtc::SMEM_BYTES, st, tmA, tmB, M, N, K, alpha, beta, C, ldc);
-  return DS2_OK;
+  if (a_mn && b_mn) return launch_gemm_tc<true, true>(tmA, tmB, M, N, K, alpha, beta, C, ldc, st);
+  if (a_mn) return launch_gemm_tc<true, false>(tmA, tmB, M, N, K, alpha, beta, C, ldc, st);
+  if (b_mn) return launch_gemm_tc<false, true>(tmA, tmB, M, N, K, alpha, beta, C, ldc, st);
+  return launch_gemm_tc<false, false>(tmA, tmB, M, N, K, alpha, beta, C, ldc, st);
 }
 
 }  // namespace ds2

@@ -1215,7 +1215,9 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
   attrs[1].id = cudaLaunchAttributeCooperative;
   attrs[1].val.cooperative = 1;
   cfg.attrs = attrs;
-  cfg.numAttrs = 2;
+  // Nsight Compute cannot replay a cooperative cluster launch: DS2_SPLITK_NONCOOP=1 (profiling only) drops the
+  // cooperative attribute; co-residency is still checked with cudaOccupancyMaxActiveClusters below.
+  cfg.numAttrs = getenv("DS2_SPLITK_NONCOOP") ? 1 : 2;
   int max_clusters = 0;
   cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
   if (oe != cudaSuccess) { (void)cudaGetLastError(); return 1; }
@@ -1281,7 +1283,9 @@ static int launch_bwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
   attrs[1].id = cudaLaunchAttributeCooperative;
   attrs[1].val.cooperative = 1;
   cfg.attrs = attrs;
-  cfg.numAttrs = 2;
+  // Nsight Compute cannot replay a cooperative cluster launch: DS2_SPLITK_NONCOOP=1 (profiling only) drops the
+  // cooperative attribute; co-residency is still checked with cudaOccupancyMaxActiveClusters below.
+  cfg.numAttrs = getenv("DS2_SPLITK_NONCOOP") ? 1 : 2;
   int max_clusters = 0;
   cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
   if (oe != cudaSuccess) { (void)cudaGetLastError(); return 1; }
