@@ -293,8 +293,11 @@ int transpose(int R, int C, const float* in, float* out, cudaStream_t st) {
 
 static inline size_t k4(int K) { return (size_t)((K + 3) / 4 * 4); }
 
-// MN-major operands are read in place (DS2_GEMM_TRANSPOSE=1 restores the transposing path for comparison)
-static bool use_mn_major() { static int v = -1; if (v < 0) v = getenv("DS2_GEMM_TRANSPOSE") ? 0 : 1; return v == 1; }
+// EXPERIMENTAL (off): MN-major operands read in place through MN-major UMMA descriptors.  With plain
+// SWIZZLE_128B tiles the tcgen05 result is wrong for TF32 (measured: all-zero products) — 32-bit MN-major
+// operands need the 128B_BASE32B layout / CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B tiles, which this kernel
+// does not build yet.  Until then non-K-major operands are transposed into the workspace.
+static bool use_mn_major() { static int v = -1; if (v < 0) v = getenv("DS2_GEMM_MN_MAJOR") ? 1 : 0; return v == 1; }
 
 size_t gemm_tc_workspace_bytes(int transA, int transB, int M, int N, int K) {
   size_t n = 0;
