@@ -58,6 +58,8 @@ struct PersistParams {
   const float* b_hh[2];
   unsigned int* bar;    // [2][NT] per-CTA step flags (zeroed by the host): flag = number of finished steps
   int nacc, acc_cols;   // independent TMEM accumulator chains (K is dealt round-robin over them)
+  int d0;               // first direction handled by this launch (directions can be launched one at a time
+                        // when both together would not be co-resident, e.g. H = 1536)
   int* err;             // set to 1 if a barrier wait timed out
 };
 
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int d = blockIdx.x / p.NT, tile = blockIdx.x % p.NT, u0 = tile * UT;
+  const int d = p.d0 + blockIdx.x / p.NT, tile = blockIdx.x % p.NT, u0 = tile * UT;
   const int NK = H / BK;
   const int GH = G * H;
   unsigned int* ctr = p.bar + 32 * d;   // one 128-byte line per direction
@@ -494,8 +496,13 @@ static int launch_fwd_resident(const SeqArgs& a, void* ws, size_t ws_bytes, cuda
   }
   int max_blocks_per_sm = 0;
   DS2_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, kern, THREADS, smem));
-  const int grid = a.D * p.NT;
-  if (max_blocks_per_sm < 1 || grid > max_blocks_per_sm * num_sms) return 1;
+  int grid = a.D * p.NT, launches = 1;
+  if (max_blocks_per_sm < 1) return 1;
+  if (grid > max_blocks_per_sm * num_sms) {           // both directions do not fit: one launch per direction
+    if (p.NT > max_blocks_per_sm * num_sms) return 1;
+    grid = p.NT;
+    launches = a.D;
+  }
   const size_t wn = (size_t)G * a.H * a.H;
   for (int d = 0; d < a.D; ++d) {
     p.b_ih[d] = a.b_ih[d];
@@ -507,9 +514,12 @@ static int launch_fwd_resident(const SeqArgs& a, void* ws, size_t ws_bytes, cuda
     if (rc) return rc;
   }
   DS2_CHECK_CUDA(cudaMemsetAsync(ws, 0, 4096, st));
-  void* args[] = {&p};
-  DS2_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(THREADS), args, smem, st));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  for (int li = 0; li < launches; ++li) {
+    p.d0 = li;
+    void* args[] = {&p};
+    DS2_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(THREADS), args, smem, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   return DS2_OK;
 }
 
@@ -543,8 +553,13 @@ static int launch_fwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t 
   }
   if (smem > 227 * 1024) return 1;
   DS2_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, kern, THREADS, smem));
-  const int grid = a.D * p.NT;
-  if (max_blocks_per_sm < 1 || grid > max_blocks_per_sm * num_sms) return 1;   // cannot be co-resident
+  int grid = a.D * p.NT, launches = 1;
+  if (max_blocks_per_sm < 1) return 1;
+  if (grid > max_blocks_per_sm * num_sms) {           // both directions do not fit: one launch per direction
+    if (p.NT > max_blocks_per_sm * num_sms) return 1;
+    grid = p.NT;
+    launches = a.D;
+  }   // cannot be co-resident
   for (int d = 0; d < a.D; ++d) {
     p.b_ih[d] = a.b_ih[d];
     p.b_hh[d] = a.b_hh[d];
@@ -554,9 +569,12 @@ static int launch_fwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t 
     if (rc) return rc;
   }
   DS2_CHECK_CUDA(cudaMemsetAsync(ws, 0, 4096, st));
-  void* args[] = {&p};
-  DS2_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(THREADS), args, smem, st));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  for (int li = 0; li < launches; ++li) {
+    p.d0 = li;
+    void* args[] = {&p};
+    DS2_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(THREADS), args, smem, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   return DS2_OK;
 }
 
@@ -593,7 +611,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int d = blockIdx.x / p.NT, tile = blockIdx.x % p.NT, u0 = tile * UT;
+  const int d = p.d0 + blockIdx.x / p.NT, tile = blockIdx.x % p.NT, u0 = tile * UT;
   const int GH = G * H;
   const int NK = GH / BK;
   unsigned int* ctr = p.bar + 32 * d;   // one 128-byte line per direction
@@ -833,7 +851,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
   const int ks = blockIdx.x & 3;                          // rank in the cluster == K split
   const int cl = blockIdx.x >> 2;
   const int NTc = H / UM;                                 // clusters per direction
-  const int d = cl / NTc, ut = cl % NTc;
+  const int d = p.d0 + cl / NTc, ut = cl % NTc;
   const int GH = G * H;
   const int Kc = GH / 4, NK = Kc / BK;
   const int kbase = ks * Kc;
@@ -1203,7 +1221,7 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
     DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
-  const int grid = a.D * p.NT * 4;
+  int grid = a.D * p.NT * 4, launches = 1;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(THREADS);
@@ -1221,7 +1239,12 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
   int max_clusters = 0;
   cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
   if (oe != cudaSuccess) { (void)cudaGetLastError(); return 1; }
-  if (max_clusters * 4 < grid) return 1;
+  if (max_clusters * 4 < grid) {
+    if (max_clusters * 4 < p.NT * 4) return 1;
+    grid = p.NT * 4;
+    launches = a.D;
+    cfg.gridDim = dim3(grid);
+  }
   DS2_CHECK_CUDA(cudaMemsetAsync(ws, 0, 4096 + align_up((size_t)a.D * (a.T + 1) * 4, 256), st));
   const size_t wn = (size_t)a.H * GH;
   for (int d = 0; d < a.D; ++d) {
@@ -1235,12 +1258,17 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
     DS2_LAUNCH(absmax_kernel, 64, 256, 0, st, (size_t)a.B * a.H, a.dy + (size_t)t_first * a.B * a.H,
                p.gmax + (size_t)d * (a.T + 1));
   }
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
-  if (le != cudaSuccess) {
-    (void)cudaGetLastError();
-    return 1;
+  for (int li = 0; li < launches; ++li) {
+    p.d0 = li;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
+    if (le != cudaSuccess) {
+      (void)cudaGetLastError();
+      if (li == 0) return 1;
+      set_error("resident split-K backward sweep: second launch failed: %s", cudaGetErrorString(le));
+      return DS2_ERR_CUDA;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
   }
-  g_launches.fetch_add(1, std::memory_order_relaxed);
   return DS2_OK;
 }
 
@@ -1271,7 +1299,7 @@ static int launch_bwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
     DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
-  const int grid = a.D * p.NT * 4;
+  int grid = a.D * p.NT * 4, launches = 1;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(THREADS);
@@ -1289,7 +1317,12 @@ static int launch_bwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
   int max_clusters = 0;
   cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
   if (oe != cudaSuccess) { (void)cudaGetLastError(); return 1; }
-  if (max_clusters * 4 < grid) return 1;                 // all clusters must be co-resident (grid barrier)
+  if (max_clusters * 4 < grid) {                         // all clusters must be co-resident (grid barrier)
+    if (max_clusters * 4 < p.NT * 4) return 1;
+    grid = p.NT * 4;                                     // one launch per direction
+    launches = a.D;
+    cfg.gridDim = dim3(grid);
+  }
   for (int d = 0; d < a.D; ++d) {
     int rc = make_tmap_2d(&p.tmW[d], a.w_hh[d], a.H, GH, GH, 64, BK);   // W_hh^T (H, G*H): 64 unit rows per box
     if (rc) return rc;
@@ -1301,12 +1334,17 @@ static int launch_bwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
     }
   }
   DS2_CHECK_CUDA(cudaMemsetAsync(ws, 0, 4096, st));
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
-  if (le != cudaSuccess) {
-    (void)cudaGetLastError();
-    return 1;                                            // e.g. cooperative+cluster launch refused: use the 16-unit kernel
+  for (int li = 0; li < launches; ++li) {
+    p.d0 = li;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
+    if (le != cudaSuccess) {
+      (void)cudaGetLastError();
+      if (li == 0) return 1;                             // e.g. cooperative+cluster launch refused: 16-unit kernel
+      set_error("split-K backward sweep: second launch failed: %s", cudaGetErrorString(le));
+      return DS2_ERR_CUDA;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
   }
-  g_launches.fetch_add(1, std::memory_order_relaxed);
   return DS2_OK;
 }
 
@@ -1338,8 +1376,13 @@ static int launch_bwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t 
   if (smem > 227 * 1024) return 1;
   int max_blocks_per_sm = 0;
   DS2_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, kern, THREADS, smem));
-  const int grid = a.D * p.NT;
-  if (max_blocks_per_sm < 1 || grid > max_blocks_per_sm * num_sms) return 1;
+  int grid = a.D * p.NT, launches = 1;
+  if (max_blocks_per_sm < 1) return 1;
+  if (grid > max_blocks_per_sm * num_sms) {           // both directions do not fit: one launch per direction
+    if (p.NT > max_blocks_per_sm * num_sms) return 1;
+    grid = p.NT;
+    launches = a.D;
+  }
   for (int d = 0; d < a.D; ++d) {
     // a.w_hh[d] is the transposed recurrent matrix (H, G*H) here
     int rc = make_tmap_2d(&p.tmW[d], a.w_hh[d], a.H, GH, GH, UT, BK);
@@ -1353,9 +1396,12 @@ static int launch_bwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t 
     }
   }
   DS2_CHECK_CUDA(cudaMemsetAsync(ws, 0, 4096, st));
-  void* args[] = {&p};
-  DS2_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(THREADS), args, smem, st));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  for (int li = 0; li < launches; ++li) {
+    p.d0 = li;
+    void* args[] = {&p};
+    DS2_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(THREADS), args, smem, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   return DS2_OK;
 }
 

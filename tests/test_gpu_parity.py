@@ -271,3 +271,37 @@ def test_tf32_full_size_properties_librispeech_layer():
         if L < T:
             assert float(y[L:, b].abs().max()) == 0.0
     assert rel(y, outs["fp32"][0]) < 5e-3 and rel(hn, outs["fp32"][1]) < 5e-3
+
+
+def test_tf32_stress_shape_h1536_one_launch_per_direction():
+    """BASELINE configs[4] layer shape (H=1536, B=8): 2 x 96 CTAs do not fit on 148 SMs, so the persistent sweeps are
+    launched one direction at a time; result must agree with the FFMA step kernels, masked frames stay exactly 0."""
+    from deepspeech_pytorch_b200 import _lib
+    T, B, In, H = 40, 8, 1536, 1536
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(T, B, In, generator=g).cuda()
+    lens = torch.tensor([40, 40, 37, 33, 30, 22, 15, 9], dtype=torch.int32)
+    for b in range(B):
+        x[int(lens[b]):, b] = 0
+    k = 1.0 / H ** 0.5
+    ws = [((torch.rand(s, generator=g) * 2 - 1) * k).cuda().requires_grad_(True) for s in
+          [(4 * H, In), (4 * H, H), (4 * H,), (4 * H,)] * 2]
+    dy = torch.randn(T, B, H, generator=g).cuda()
+    res = {}
+    for prec in ("tf32", "fp32"):
+        ds.set_precision(prec)
+        for w in ws:
+            w.grad = None
+        xx = x.clone().requires_grad_(True)
+        y, hn, cn = ds.ops.RnnLayer.apply(xx, lens.cuda(), _lib.RNN_LSTM, True, True, 0.1, 1e-5, None, None, None,
+                                          None, None, None, *ws)
+        y.backward(dy)
+        res[prec] = (y.detach(), hn.detach(), xx.grad.clone(), [w.grad.clone() for w in ws])
+    a, b_ = res["tf32"], res["fp32"]
+    for bb in range(B):
+        L = int(lens[bb])
+        if L < T:
+            assert float(a[0][L:, bb].abs().max()) == 0.0
+    assert rel(a[0], b_[0]) < 5e-3 and rel(a[1], b_[1]) < 5e-3 and rel_l2(a[2], b_[2]) < 1e-2
+    for ga, gb in zip(a[3], b_[3]):
+        assert rel_l2(ga, gb) < 1e-2
