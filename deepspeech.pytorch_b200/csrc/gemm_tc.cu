@@ -6,9 +6,10 @@
 //               (M=128, N=256, K=8) x4 per stage, accumulating in TMEM; tcgen05.commit frees the stage
 //   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> alpha/beta -> global
 //
-// Operands that are not K-major in memory (transA / !transB) are first transposed into the
-// workspace by a tiled transpose kernel (a few % of the GEMM time at the shapes of this path).
+// Operands that are not K-major in memory (transA / !transB) are read in place as MN-major tiles
+// (SWIZZLE_128B_BASE32B, see smem_desc_mn); unaligned ones are first transposed into the workspace.
 // Shapes the kernel does not take (tiny or unaligned) return 1 and the caller uses the FFMA GEMM.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -41,7 +42,13 @@ static int load_encode() {
   return DS2_OK;
 }
 
+static int make_tmap_2d_sw(CUtensorMap* out, const float* base, int rows, int cols, int ld, int box_rows, int box_cols,
+                           CUtensorMapSwizzle sw);
 int make_tmap_2d(CUtensorMap* out, const float* base, int rows, int cols, int ld, int box_rows, int box_cols) {
+  return make_tmap_2d_sw(out, base, rows, cols, ld, box_rows, box_cols, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+static int make_tmap_2d_sw(CUtensorMap* out, const float* base, int rows, int cols, int ld, int box_rows, int box_cols,
+                           CUtensorMapSwizzle sw) {
   int rc = load_encode();
   if (rc) return rc;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -49,7 +56,7 @@ int make_tmap_2d(CUtensorMap* out, const float* base, int rows, int cols, int ld
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(out, g_tmap_dtype, 2, const_cast<float*>(base), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(2d rows=%d cols=%d ld=%d box=%dx%d base=%p) failed: %d", rows, cols, ld,
@@ -141,24 +148,29 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*b
 constexpr int THREADS = 192;
 }  // namespace gtc
 
-// MN-major operand tile (the matrix is stored (K, MN) row-major, i.e. "transposed" for this GEMM): the tile is
-// loaded as ROWS/32 TMA boxes of (32 mn x 32 k): box i occupies 4 KB = 32 k-rows of 128 bytes, 8-row groups are
-// 1024 B apart (stride byte offset), consecutive 32-wide MN atoms are 4096 B apart (leading byte offset); an
-// MMA (K = 8) consumes one 8-row group, so the k-step advance is 1024 B.  No transpose pass is needed.
-__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// MN-major operand tile (the matrix is stored (K, MN) row-major, i.e. "transposed" for this GEMM).  32-bit
+// MN-major operands have exactly one legal shared-memory layout on tcgen05, SWIZZLE_128B_BASE32B (descriptor
+// layout type 1; with the plain 128B swizzle the MMA returns zeros): rows of 32 mn elements (128 B), the
+// 32-byte chunk index of a row XOR-ed with (k & 3), repeating every 4 k-rows (512 B) — what the TMA unit
+// produces with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  The tile is loaded as ROWS/32 boxes of (32 mn x 32 k):
+// box i occupies 4 KB; leading byte offset = distance between consecutive 32-wide MN blocks (4096), stride byte
+// offset = distance between 4-row k groups (512); one MMA (K = 8) consumes two groups, so the k-step advance
+// is 1024 B.  No transpose pass is needed.
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t smem_addr, uint32_t layout, uint32_t lbo_bytes,
+                                                 uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)(lbo_bytes >> 4) << 16;
   d |= (uint64_t)(sbo_bytes >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(gtc::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-               float alpha, float beta, float* __restrict__ C, int ldc, int swap_lbo_sbo) {
+               float alpha, float beta, float* __restrict__ C, int ldc, unsigned int mn_cfg) {
   using namespace gtc;
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
@@ -210,15 +222,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = instr_desc(FMT_TF32, BM, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
-      const uint32_t lbo = swap_lbo_sbo ? 1024u : 4096u, sbo = swap_lbo_sbo ? 4096u : 1024u;
+      const uint32_t mn_layout = mn_cfg & 7u, lbo = ((mn_cfg >> 4) & 0x3FFFu) << 4, sbo = (mn_cfg >> 18) << 4;
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES), b_addr = smem_u32(smem + s * STAGE_BYTES + A_BYTES);
-        const uint64_t adesc = A_MN ? smem_desc_sw128_mn(a_addr, lbo, sbo) : smem_desc_sw128(a_addr);
-        const uint64_t bdesc = B_MN ? smem_desc_sw128_mn(b_addr, lbo, sbo) : smem_desc_sw128(b_addr);
+        const uint64_t adesc = A_MN ? smem_desc_mn(a_addr, mn_layout, lbo, sbo) : smem_desc_sw128(a_addr);
+        const uint64_t bdesc = B_MN ? smem_desc_mn(b_addr, mn_layout, lbo, sbo) : smem_desc_sw128(b_addr);
         // k-step: K-major +32 B inside the 128B swizzle row; MN-major +1024 B (the next group of 8 k-rows)
         constexpr uint64_t a_adv = A_MN ? 64 : 2, b_adv = B_MN ? 64 : 2;
 #pragma unroll
@@ -293,11 +305,18 @@ int transpose(int R, int C, const float* in, float* out, cudaStream_t st) {
 
 static inline size_t k4(int K) { return (size_t)((K + 3) / 4 * 4); }
 
-// EXPERIMENTAL (off): MN-major operands read in place through MN-major UMMA descriptors.  With plain
-// SWIZZLE_128B tiles the tcgen05 result is wrong for TF32 (measured: all-zero products) — 32-bit MN-major
-// operands need the 128B_BASE32B layout / CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B tiles, which this kernel
-// does not build yet.  Until then non-K-major operands are transposed into the workspace.
-static bool use_mn_major() { static int v = -1; if (v < 0) v = getenv("DS2_GEMM_MN_MAJOR") ? 1 : 0; return v == 1; }
+// MN-major operands are read in place (no transpose pass); DS2_GEMM_MN_MAJOR=0 restores the transposes;
+// DS2_GEMM_MN_CFG="tma_swizzle,layout,lbo,sbo" overrides the tile layout parameters (bring-up only).
+struct MnCfg { int on, sw, layout, lbo, sbo; };
+static MnCfg mn_cfg_from_env() {
+  MnCfg c{1, (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 1, 4096, 512};
+  const char* e = getenv("DS2_GEMM_MN_MAJOR");
+  if (e) c.on = atoi(e);
+  const char* f = getenv("DS2_GEMM_MN_CFG");
+  if (f) sscanf(f, "%d,%d,%d,%d", &c.sw, &c.layout, &c.lbo, &c.sbo);
+  return c;
+}
+static bool use_mn_major() { return mn_cfg_from_env().on != 0; }
 
 size_t gemm_tc_workspace_bytes(int transA, int transB, int M, int N, int K) {
   size_t n = 0;
@@ -317,10 +336,10 @@ static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M,
     DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gtc::SMEM_BYTES));
     attr_set = true;
   }
-  static int swap = -1;
-  if (swap < 0) swap = getenv("DS2_GEMM_SWAP_LBO_SBO") ? 1 : 0;
+  const MnCfg mc = mn_cfg_from_env();
+  const unsigned int mn_cfg = (unsigned)(mc.layout & 7) | ((unsigned)(mc.lbo >> 4) << 4) | ((unsigned)(mc.sbo >> 4) << 18);
   dim3 grid(cdiv(N, gtc::BN), cdiv(M, gtc::BM));
-  DS2_LAUNCH(kern, grid, gtc::THREADS, gtc::SMEM_BYTES, st, tmA, tmB, M, N, K, alpha, beta, C, ldc, swap);
+  DS2_LAUNCH(kern, grid, gtc::THREADS, gtc::SMEM_BYTES, st, tmA, tmB, M, N, K, alpha, beta, C, ldc, mn_cfg);
   return DS2_OK;
 }
 
@@ -361,9 +380,10 @@ int gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const floa
     return 1;
   CUtensorMap tmA, tmB;
   // K-major: matrix [rows, K] box (32 k, rows) ; MN-major: matrix [K, rows] box (32 rows, 32 k)
-  int rc = a_mn ? make_tmap_2d(&tmA, Ak, K, M, ldak, 32, 32) : make_tmap_2d(&tmA, Ak, M, K, ldak, gtc::BM, gtc::BK);
+  const CUtensorMapSwizzle mn_sw = (CUtensorMapSwizzle)mn_cfg_from_env().sw;
+  int rc = a_mn ? make_tmap_2d_sw(&tmA, Ak, K, M, ldak, 32, 32, mn_sw) : make_tmap_2d(&tmA, Ak, M, K, ldak, gtc::BM, gtc::BK);
   if (rc) return rc;
-  rc = b_mn ? make_tmap_2d(&tmB, Bk, K, N, ldbk, 32, 32) : make_tmap_2d(&tmB, Bk, N, K, ldbk, gtc::BN, gtc::BK);
+  rc = b_mn ? make_tmap_2d_sw(&tmB, Bk, K, N, ldbk, 32, 32, mn_sw) : make_tmap_2d(&tmB, Bk, N, K, ldbk, gtc::BN, gtc::BK);
   if (rc) return rc;
   if (a_mn && b_mn) return launch_gemm_tc<true, true>(tmA, tmB, M, N, K, alpha, beta, C, ldc, st);
   if (a_mn) return launch_gemm_tc<true, false>(tmA, tmB, M, N, K, alpha, beta, C, ldc, st);

@@ -58,6 +58,7 @@ struct PersistParams {
   const float* b_hh[2];
   unsigned int* bar;    // [2][NT] per-CTA step flags (zeroed by the host): flag = number of finished steps
   int nacc, acc_cols;   // independent TMEM accumulator chains (K is dealt round-robin over them)
+  int defer;            // 1: stores that only later kernels read are issued after the barrier arrival
   int d0;               // first direction handled by this launch (directions can be launched one at a time
                         // when both together would not be co-resident, e.g. H = 1536)
   int* err;             // set to 1 if a barrier wait timed out
@@ -71,7 +72,11 @@ __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
 __device__ __forceinline__ void red_release(unsigned int* p, unsigned int v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Cross-proxy ordering for data that one CTA writes with ordinary stores and another CTA reads with TMA.  The
+// unqualified fence.proxy.async compiles to MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC (measured ~950 cycles per call inside
+// the sweeps, three of them on the per-step critical path); the .global form is the proxy fence alone, and the
+// gpu-scope ordering comes from the release / acquire pair on the barrier counter, which is needed anyway.
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // Grid barrier of one direction: every CTA publishes the number of steps it has finished in its own
 // 4-byte flag (plain release store, no atomic serialisation); a whole warp polls all NT flags
@@ -106,30 +111,47 @@ __device__ __forceinline__ void grid_wait_flags(const unsigned int* flags, int n
   asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire side of the flag protocol
 }
 // single-thread variant on a monotonically increasing arrival counter
+// (relaxed polling loads, then one acquire fence: an acquire load would invalidate L1 on every poll)
 __device__ __forceinline__ void grid_wait_counter(const unsigned int* ctr, unsigned int target, int* err) {
-  if (ld_acquire(ctr) >= target) return;
-  const long long t0 = clock64();
-  unsigned int it = 0;
-  while (ld_acquire(ctr) < target) {
-    if ((++it & 255u) == 0) {
-      if (*(volatile int*)err) return;
-      if (clock64() - t0 > rp::SPIN_LIMIT) {
-        *(volatile int*)err = 1;
-        printf("ds2: recurrent sweep barrier timeout (block %d, target %u, have %u)\n", blockIdx.x, target,
-               ld_acquire(ctr));
-        return;
+  if (ld_relaxed(ctr) < target) {
+    const long long t0 = clock64();
+    unsigned int it = 0;
+    while (ld_relaxed(ctr) < target) {
+      if ((++it & 255u) == 0) {
+        if (*(volatile int*)err) break;
+        if (clock64() - t0 > rp::SPIN_LIMIT) {
+          *(volatile int*)err = 1;
+          printf("ds2: recurrent sweep barrier timeout (block %d, target %u, have %u)\n", blockIdx.x, target,
+                 ld_relaxed(ctr));
+          break;
+        }
       }
     }
   }
+  asm volatile("fence.acquire.gpu;" ::: "memory");
 }
 __device__ __forceinline__ void st_release(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.f, fast_sigmoid(2.f * x), -1.f); }
+// MUFU.EX2 / MUFU.RCP without the denormal-range fix-up code of the CUDA fast-math intrinsics (that code
+// serialises independent chains through one predicate register); inputs are gate pre-activations.
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+constexpr float LOG2E = 1.4426950408889634f;
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_ftz(1.f + ex2_ftz(-LOG2E * x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.f, rcp_ftz(1.f + ex2_ftz(-2.f * LOG2E * x)), -1.f); }
 
-__device__ __forceinline__ void trace_stamp(long long* trace, int step, int slot) {
-  if (trace && blockIdx.x == 0) trace[(size_t)step * 6 + slot] = clock64();
+// debug trace: 16 clock64 slots per (CTA, step); slot 12 holds %globaltimer (ns) instead
+constexpr int TRACE_SLOTS = 16;
+__device__ __forceinline__ void trace_stamp(long long* trace, int T, int step, int slot) {
+  if (trace) trace[((size_t)blockIdx.x * T + step) * TRACE_SLOTS + slot] = clock64();
+}
+__device__ __forceinline__ void trace_stamp_ns(long long* trace, int T, int step, int slot) {
+  if (trace) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    trace[((size_t)blockIdx.x * T + step) * TRACE_SLOTS + slot] = (long long)ns;
+  }
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -147,7 +169,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
   using namespace tc;
   constexpr int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB aligned, still __shared__
   const int NB = p.NB, B = p.B, T = p.T, H = p.H, D = p.D;
   const int B_BYTES = NB * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   const int NBp = NB + 1;
@@ -207,14 +229,15 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
           // the previous step's MMAs have finished reading hbuf: this CTA's epilogue (which waited for them)
           // arrived at the barrier we are about to pass
           grid_wait_counter(ctr, (unsigned int)p.NT * (unsigned int)step, p.err);
-          fence_proxy_async_all();
-          trace_stamp(p.trace, step, 0);
+          fence_proxy_async_global();
+          trace_stamp(p.trace, p.T, step, 0);
           for (int g = 0; g * 4 < NKR; ++g) {  // one mbarrier per group of 4 chunks (256 k)
             uint64_t* fb = full + g;
             const int c0 = g * 4, c1 = min(NKR, c0 + 4);
             mbar_arrive_expect_tx(fb, (uint32_t)((c1 - c0) * B * 128));
             for (int c = c0; c < c1; ++c) tma_load_2d(hbuf + c * B_BYTES, &p.tmV[d], fb, c * 64, tp * B);
           }
+          trace_stamp(p.trace, p.T, step, 1);
         }
       }
     } else
@@ -232,8 +255,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
           tma_load_3d(smem + s * STAGE_BYTES, &p.tmW[d], &full[s], c * BK, u0, 0);
           if (c == 0) {
             grid_wait_counter(ctr, (unsigned int)p.NT * (unsigned int)step, p.err);
-            fence_proxy_async_all();
-            trace_stamp(p.trace, step, 0);
+            fence_proxy_async_global();
+            trace_stamp(p.trace, p.T, step, 0);
           }
           tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &p.tmV[d], &full[s], c * BK, tp * B);
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -253,9 +276,9 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
           for (int g = 0; g * 4 < NKR; ++g) {
             mbar_wait(full + g, ph);
             tc_fence_after();
-            if (g == 0) trace_stamp(p.trace, step, 1);
+            if (g == 0) trace_stamp(p.trace, p.T, step, 2);
             const int c0 = g * 4, c1 = min(NKR, c0 + 4);
-            if (c1 == NKR) trace_stamp(p.trace, step, 2);
+            if (c1 == NKR) trace_stamp(p.trace, p.T, step, 3);
             for (int c = c0; c < c1; ++c) {
               const uint64_t ad = a_base + (uint64_t)c * a_step, bd = b_base + (uint64_t)c * b_step;
               mma_f16(0u, ad, bd, idesc, c > 0);
@@ -265,6 +288,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
             }
           }
           mma_commit(accum_bar);
+          trace_stamp(p.trace, p.T, step, 4);
           ph ^= 1;
         }
       }
@@ -282,8 +306,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
       for (int step = 1; step < T; ++step) {
         for (int c = 0; c < NK; ++c) {
           mbar_wait(&full[s], ph);
-          if (c == 0) trace_stamp(p.trace, step, 1);
-          if (c == NK - 1) trace_stamp(p.trace, step, 2);
+          if (c == 0) trace_stamp(p.trace, p.T, step, 1);
+          if (c == NK - 1) trace_stamp(p.trace, p.T, step, 2);
           tc_fence_after();
           const uint64_t ad = a_base + (uint64_t)s * stage_step, bd = b_base + (uint64_t)s * stage_step;
           mma_tf32(0u, ad, bd, idesc, c > 0);
@@ -322,7 +346,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
         }
         float a16[16];
         if (step > 0 && q < G) {
-          if (cb == 0) { mbar_wait(accum_bar, acc_phase); tc_fence_after(); if (e == 0) trace_stamp(p.trace, step, 3); }
+          if (cb == 0) { mbar_wait(accum_bar, acc_phase); tc_fence_after(); if (e == 0) trace_stamp(p.trace, p.T, step, 5); }
           float acc[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, acc);
 #pragma unroll
@@ -334,70 +358,148 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
 #pragma unroll
           for (int j = 0; j < 16; ++j) a16[j] = 0.f;
         }
+        // The gate of a warp is uniform: v = sc * sigmoid(sc * pre) + (1 - sc) is the sigmoid for sc = 1 and tanh
+        // for sc = 2, i.e. one EX2 + one RCP per value.  The 16 values of a lane are processed stage by stage so
+        // that the special-function latencies overlap (the straightforward per-value form was compiled into two
+        // serial chains and cost ~2200 cycles per step on the critical path).
+        float v[16];
+        const bool act = RNN == DS2_RNN_LSTM || (RNN == DS2_RNN_GRU && q < 2) || (RNN == DS2_RNN_TANH && q == 0);
+        if (act) {
+          const float sc = ((RNN == DS2_RNN_LSTM && q == 2) || RNN == DS2_RNN_TANH) ? 2.f : 1.f;
+          const float bsum = bias_x + bias_h, nsc = -sc * LOG2E, off = 1.f - sc;
+          float ev[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ev[j] = ex2_ftz(nsc * ((gx[j] + a16[j]) + bsum));
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ev[j] = rcp_ftz(1.f + ev[j]);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(sc, ev[j], off);
+        } else if (RNN == DS2_RNN_GRU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = q == 2 ? a16[j] + bias_h      // W_hn h + b_hn
+                                                     : gx[j] + bias_x;      // x_n + b_in
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int b = cb + half * 16 + j;
-          float v;
-          if (RNN == DS2_RNN_LSTM) {
-            const float pre = gx[j] + bias_x + a16[j] + bias_h;
-            v = (q == 2) ? fast_tanh(pre) : fast_sigmoid(pre);
-          } else if (RNN == DS2_RNN_GRU) {
-            if (q < 2) v = fast_sigmoid(gx[j] + bias_x + a16[j] + bias_h);
-            else if (q == 2) v = a16[j] + bias_h;          // W_hn h + b_hn
-            else v = gx[j] + bias_x;                       // x_n + b_in
-          } else {
-            v = (q == 0) ? fast_tanh(gx[j] + bias_x + a16[j] + bias_h) : 0.f;
-          }
-          if (b < B) ex[(q * UT + ul) * NBp + b] = v;
+          if (b < B) ex[(q * UT + ul) * NBp + b] = v[j];
         }
       }
       if (step > 0) acc_phase ^= 1;
       tc_fence_before();
+      if (e == 0) trace_stamp(p.trace, p.T, step, 6);
       named_bar_sync(1, 128);
-      if (e == 0) trace_stamp(p.trace, step, 4);
-      // ---------------- combine: (unit, batch) pairs over the 128 epilogue threads
-      for (int pi = e; pi < UT * B; pi += 128) {
-        const int ui = pi % UT, b = pi / UT;
-        const bool valid = t < lens_s[b];
-        const size_t so = (((size_t)d * T + t) * B + b) * H + u0 + ui;
-        float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + ui;
-        const float e0 = ex[(0 * UT + ui) * NBp + b], e1 = ex[(1 * UT + ui) * NBp + b];
-        const float e2 = ex[(2 * UT + ui) * NBp + b], e3 = ex[(3 * UT + ui) * NBp + b];
-        float hval = 0.f;
+      if (e == 0) trace_stamp(p.trace, p.T, step, 7);
+      // ---------------- combine: (unit, batch) pairs over the 128 epilogue threads, four pairs per thread at a
+      // time and stage by stage (independent special-function chains).  Only the fp16 copy of h_t (resident
+      // variant) is read by the next step; the fp32 outputs (sequence output, saved activations / cell state for
+      // the backward) are returned in o[] so that the caller can store them after the barrier arrival.
+      constexpr int NDF = 4;
+      auto combine4 = [&](int base, float (&o)[NDF][6]) {
+        float e0[NDF], e1[NDF], e2[NDF], e3[NDF], cp[NDF], hval[NDF];
+        int ci[NDF];
+        bool in[NDF], valid[NDF];
+#pragma unroll
+        for (int j = 0; j < NDF; ++j) {
+          const int pi = base + 128 * j;
+          in[j] = pi < UT * B;
+          const int ui = in[j] ? pi % UT : 0, b = in[j] ? pi / UT : 0;
+          valid[j] = in[j] && t < lens_s[b];
+          ci[j] = ui * NBp + b;
+          e0[j] = ex[(0 * UT + ui) * NBp + b]; e1[j] = ex[(1 * UT + ui) * NBp + b];
+          e2[j] = ex[(2 * UT + ui) * NBp + b]; e3[j] = ex[(3 * UT + ui) * NBp + b];
+          cp[j] = cst[ci[j]];
+        }
         if (RNN == DS2_RNN_LSTM) {
-          float cval = 0.f;
-          if (valid) {
-            cval = fmaf(e1, cst[ui * NBp + b], e0 * e2);
-            hval = e3 * fast_tanh(cval);
-            cst[ui * NBp + b] = cval;
-          }
-          p.aux[so] = cval;
-          if (p.training) {
-            gp[0] = valid ? e0 : 0.f; gp[H] = valid ? e1 : 0.f; gp[2 * H] = valid ? e2 : 0.f;
-            gp[3 * H] = valid ? e3 : 0.f;
+          float cval[NDF], th[NDF];
+#pragma unroll
+          for (int j = 0; j < NDF; ++j) cval[j] = valid[j] ? fmaf(e1[j], cp[j], e0[j] * e2[j]) : 0.f;
+#pragma unroll
+          for (int j = 0; j < NDF; ++j) th[j] = ex2_ftz(-2.f * LOG2E * cval[j]);
+#pragma unroll
+          for (int j = 0; j < NDF; ++j) th[j] = rcp_ftz(1.f + th[j]);
+#pragma unroll
+          for (int j = 0; j < NDF; ++j) {
+            hval[j] = valid[j] ? e3[j] * fmaf(2.f, th[j], -1.f) : 0.f;
+            if (valid[j]) cst[ci[j]] = cval[j];
+            o[j][0] = valid[j] ? e0[j] : 0.f; o[j][1] = valid[j] ? e1[j] : 0.f;
+            o[j][2] = valid[j] ? e2[j] : 0.f; o[j][3] = valid[j] ? e3[j] : 0.f;
+            o[j][4] = cval[j];
           }
         } else if (RNN == DS2_RNN_GRU) {
-          float nval = 0.f;
-          if (valid) {
-            const float hprev = cst[ui * NBp + b];
-            nval = fast_tanh(fmaf(e0, e2, e3));
-            hval = fmaf(e1, hprev - nval, nval);
-            cst[ui * NBp + b] = hval;
+          float th[NDF];
+#pragma unroll
+          for (int j = 0; j < NDF; ++j) th[j] = ex2_ftz(-2.f * LOG2E * fmaf(e0[j], e2[j], e3[j]));
+#pragma unroll
+          for (int j = 0; j < NDF; ++j) th[j] = rcp_ftz(1.f + th[j]);
+#pragma unroll
+          for (int j = 0; j < NDF; ++j) {
+            const float nval = valid[j] ? fmaf(2.f, th[j], -1.f) : 0.f;
+            hval[j] = valid[j] ? fmaf(e1[j], cp[j] - nval, nval) : 0.f;
+            if (valid[j]) cst[ci[j]] = hval[j];
+            o[j][0] = valid[j] ? e0[j] : 0.f; o[j][1] = valid[j] ? e1[j] : 0.f; o[j][2] = nval; o[j][3] = 0.f;
+            o[j][4] = valid[j] ? e2[j] : 0.f;
           }
-          p.aux[so] = valid ? e2 : 0.f;
-          if (p.training) { gp[0] = valid ? e0 : 0.f; gp[H] = valid ? e1 : 0.f; gp[2 * H] = nval; }
         } else {
-          hval = valid ? e0 : 0.f;
-          if (p.training) gp[0] = hval;
+#pragma unroll
+          for (int j = 0; j < NDF; ++j) {
+            hval[j] = valid[j] ? e0[j] : 0.f;
+            o[j][0] = hval[j]; o[j][1] = o[j][2] = o[j][3] = o[j][4] = 0.f;
+          }
         }
-        p.hseq[so] = hval;
-        if (RES) p.h16[so] = __float2half_rn(hval);
+#pragma unroll
+        for (int j = 0; j < NDF; ++j) {
+          o[j][5] = hval[j];
+          if (RES && in[j]) {
+            const int pi = base + 128 * j;
+            p.h16[(((size_t)d * T + t) * B + pi / UT) * H + u0 + pi % UT] = __float2half_rn(hval[j]);
+          }
+        }
+      };
+      auto store_pair = [&](int pi, const float (&o)[6]) {
+        const int ui = pi % UT, b = pi / UT;
+        const size_t so = (((size_t)d * T + t) * B + b) * H + u0 + ui;
+        float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + ui;
+        if (RNN != DS2_RNN_TANH) p.aux[so] = o[4];
+        if (p.training) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) gp[g * H] = o[g];
+        }
+        p.hseq[so] = o[5];
+      };
+      const bool defer = RES && p.defer && UT * B <= 128 * NDF;
+      float sv[NDF][6];
+      if (defer) {
+        combine4(e, sv);
+      } else {
+        for (int base = e; base < UT * B; base += 128 * NDF) {
+          combine4(base, sv);
+#pragma unroll
+          for (int j = 0; j < NDF; ++j)
+            if (base + 128 * j < UT * B) store_pair(base + 128 * j, sv[j]);
+        }
       }
+      if (e == 0) trace_stamp(p.trace, p.T, step, 8);
       named_bar_sync(1, 128);          // CTA-scope: every epilogue thread's stores happen-before thread 0's release
       if (e == 0) {
-        fence_proxy_async_all();
-        red_release(ctr, 1u);            // release is cumulative over the stores ordered by the named barrier
-        trace_stamp(p.trace, step, 5);
+        trace_stamp(p.trace, p.T, step, 9);
+        fence_proxy_async_global();
+        trace_stamp(p.trace, p.T, step, 10);
+        // release is cumulative over the stores ordered by the named barrier
+        red_release(ctr, 1u);
+        trace_stamp(p.trace, p.T, step, 11);
+        trace_stamp_ns(p.trace, p.T, step, 12);
+      }
+      if (defer) {
+#pragma unroll
+        for (int j = 0; j < NDF; ++j) {
+          const int pi = e + 128 * j;
+          if (pi < UT * B) store_pair(pi, sv[j]);
+        }
+        if (e == 0) trace_stamp(p.trace, p.T, step, 13);
       }
     }
   }
@@ -418,6 +520,13 @@ static long long* trace_ptr_from_env(const char* name) {
   const char* e = getenv(name);   // debug: device address of an int64 buffer of 6*T entries
   return e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 10)) : nullptr;
 }
+
+static int env_flag(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+// DS2_SWEEP_DEFER=0: store everything before the barrier arrival (see PersistParams::defer)
+static int sweep_defer_default() { return env_flag("DS2_SWEEP_DEFER", 1); }
 
 static size_t fwd_smem_bytes(int NB) {
   using namespace rp;
@@ -477,6 +586,7 @@ static int launch_fwd_resident(const SeqArgs& a, void* ws, size_t ws_bytes, cuda
   p.training = a.training;
   p.len = a.len; p.gates = a.gates; p.hseq = a.hseq; p.aux = a.aux;
   p.trace = trace_ptr_from_env("DS2_TRACE_FWD");
+  p.defer = sweep_defer_default();
   set_acc_layout(p);
   p.err = static_cast<int*>(ws);
   p.bar = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + 128);
@@ -599,7 +709,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
   using namespace tc;
   constexpr int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB aligned, still __shared__
   const int NB = p.NB, B = p.B, T = p.T, H = p.H, D = p.D;
   const int B_BYTES = NB * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   const int NBp = NB + 1;
@@ -653,8 +763,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
           tma_load_2d(smem + s * STAGE_BYTES, &p.tmW[d], &full[s], c * BK, u0);
           if (c == 0) {
             grid_wait_counter(ctr, (unsigned int)p.NT * (unsigned int)step, p.err);
-            fence_proxy_async_all();
-            trace_stamp(p.trace, step, 0);
+            fence_proxy_async_global();
+            trace_stamp(p.trace, p.T, step, 0);
           }
           const int k0 = c * BK;
           if (RNN == DS2_RNN_GRU && k0 >= 2 * H)
@@ -679,8 +789,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
       for (int step = 1; step < T; ++step) {
         for (int c = 0; c < NK; ++c) {
           mbar_wait(&full[s], ph);
-          if (c == 0) trace_stamp(p.trace, step, 1);
-          if (c == NK - 1) trace_stamp(p.trace, step, 2);
+          if (c == 0) trace_stamp(p.trace, p.T, step, 1);
+          if (c == NK - 1) trace_stamp(p.trace, p.T, step, 2);
           tc_fence_after();
           const uint64_t ad = a_base + (uint64_t)s * stage_step, bd = b_base + (uint64_t)s * stage_step;
           mma_tf32(0u, ad, bd, idesc, c > 0);
@@ -704,7 +814,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
       if (q == 0 && step > 0) {          // rows 0..15 of the accumulator live in lanes 0..15 of quarter 0
         mbar_wait(accum_bar, acc_phase);
         tc_fence_after();
-        if (lane == 0) trace_stamp(p.trace, step, 3);
+        if (lane == 0) trace_stamp(p.trace, p.T, step, 3);
         for (int cb = 0; cb < NB; cb += 32) {
           float acc[32];
           const int nsum = min(p.nacc, NK * (BK / 8));
@@ -725,7 +835,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
       if (step > 0) acc_phase ^= 1;
       tc_fence_before();
       named_bar_sync(1, 128);
-      if (e == 0) trace_stamp(p.trace, step, 4);
+      if (e == 0) trace_stamp(p.trace, p.T, step, 4);
       for (int pi = e; pi < UT * B; pi += 128) {
         const int ui = pi % UT, b = pi / UT;
         const bool valid = t < p.len[b];
@@ -759,9 +869,9 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
       }
       named_bar_sync(1, 128);          // CTA-scope: every epilogue thread's stores happen-before thread 0's release
       if (e == 0) {
-        fence_proxy_async_all();
+        fence_proxy_async_global();
         red_release(ctr, 1u);            // release is cumulative over the stores ordered by the named barrier
-        trace_stamp(p.trace, step, 5);
+        trace_stamp(p.trace, p.T, step, 5);
       }
     }
   }
@@ -776,9 +886,12 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
 // Backward sweep, split-K variant (the fast path): a 4-CTA cluster owns 64 hidden units; CTA `ks` of
 // the cluster reduces over a quarter of K = G*H, so every CTA issues the same number of MMAs per
 // step as the forward sweep with all 64 M rows useful.  The partial sums (64 units x B) are exchanged
-// through distributed shared memory: each CTA publishes its partial tile, signals the four cluster
-// peers' mbarriers (release.cluster) and then reduces + finishes the 16 units it owns (gate backward,
-// carried dc / dh in shared memory).
+// through distributed shared memory in push form: TMEM quarter q of every CTA holds the rows that CTA q
+// of the cluster finishes, so epilogue warp q sends them straight into CTA q's shared memory with
+// st.async (16-byte stores that complete_tx on the destination's mbarrier); each CTA then reduces the four
+// slices it received from its own shared memory and finishes its 16 units (gate backward, carried dc / dh).
+// (The earlier pull form — publish, cluster barrier, 4-byte ld.shared::cluster reads with a 132-byte lane
+// stride — cost ~5.9k of the 16k cycles per step.)
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
@@ -792,8 +905,9 @@ __device__ __forceinline__ float ld_dsmem(uint32_t addr) {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* err) {
+  uint32_t ok = 0, it = 0;
+  long long t0 = 0;
   while (!ok) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -802,7 +916,20 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "=r"(ok)
         : "r"(tc::smem_u32(bar)), "r"(parity)
         : "memory");
+    if (!ok && (++it & 1023u) == 0) {            // bounded: a protocol fault must not hang the GPU
+      if (t0 == 0) t0 = clock64();
+      if (*(volatile int*)err) return;
+      if (clock64() - t0 > rp::SPIN_LIMIT) { *(volatile int*)err = 1; return; }
+    }
   }
+}
+// 16-byte store into a cluster peer's shared memory that also counts 16 bytes on the peer's mbarrier
+// (st.async: data and completion travel together, no fence / separate arrive on the critical path)
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, float a, float b, float c, float d, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   cluster_addr),
+               "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_bar)
+               : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -831,14 +958,15 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
   constexpr int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
   constexpr int UM = 64;                       // units per cluster (all M rows valid)
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB aligned, still __shared__
   const int NB = p.NB, B = p.B, T = p.T, H = p.H, D = p.D;
   const int B_BYTES = NB * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   const int NBp = NB + 1;
   const int NKR = (G * H / 4) / 64;                                      // resident: 64 fp16 of K per chunk
   const int ring_bytes = RES ? NKR * STAGE_BYTES : STAGES * STAGE_BYTES;
-  float* part = reinterpret_cast<float*>(smem + ring_bytes);             // [64][NBp] partial dh_rec of this CTA
-  float* cst = part + UM * NBp;                                          // [16][NBp] carried dc / dh
+  const int PS = ((NB + 3) & ~3) + 4;                                    // row pitch of the received tiles (16 B aligned)
+  float* part = reinterpret_cast<float*>(smem + ring_bytes);             // [4 sources][16][PS] partial dh_rec
+  float* cst = part + UM * PS;                                           // [16][NBp] carried dc / dh
   int* lens_s = reinterpret_cast<int*>(cst + UT * NBp);
   unsigned int* cta_max = reinterpret_cast<unsigned int*>(lens_s + ((NB + 1) & ~1));   // [2] (8 bytes)
   uint64_t* full = reinterpret_cast<uint64_t*>(cta_max + 2);             // resident: one per group of 4 chunks
@@ -865,7 +993,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
     for (int i = 0; i < (RES ? 32 : STAGES); ++i) mbar_init(&full[i], 1);
     for (int i = 0; i < STAGES; ++i) mbar_init(&empty[i], 1);
     mbar_init(accum_bar, 1);
-    mbar_init(part_bar, 4);
+    mbar_init(part_bar, 1);
     fence_barrier_init();
     cta_max[0] = 0u;
   }
@@ -896,8 +1024,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
           const int t = d == 0 ? T - 1 - step : step;
           const int tn = d == 0 ? t + 1 : t - 1;
           grid_wait_counter(ctr, n_arrive * (unsigned int)step, p.err);
-          fence_proxy_async_all();
-          trace_stamp(p.trace, step, 0);
+          fence_proxy_async_global();
+          trace_stamp(p.trace, p.T, step, 0);
           for (int g = 0; g * 4 < NKR; ++g) {
             uint64_t* fb = full + g;
             const int c0 = g * 4, c1 = min(NKR, c0 + 4);
@@ -905,6 +1033,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
             for (int c = c0; c < c1; ++c)
               tma_load_2d(vbuf + c * B_BYTES, &p.tmV[d], fb, d * GH + kbase + c * 64, tn * B);
           }
+          trace_stamp(p.trace, p.T, step, 1);
         }
       }
     } else
@@ -921,8 +1050,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
           tma_load_2d(smem + s * STAGE_BYTES, &p.tmW[d], &full[s], k0, ut * UM);
           if (c == 0) {
             grid_wait_counter(ctr, n_arrive * (unsigned int)step, p.err);
-            fence_proxy_async_all();
-            trace_stamp(p.trace, step, 0);
+            fence_proxy_async_global();
+            trace_stamp(p.trace, p.T, step, 0);
           }
           if (RNN == DS2_RNN_GRU && k0 >= 2 * H)
             tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &p.tmV2[d], &full[s], k0 - 2 * H, tn * B);
@@ -945,9 +1074,9 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
           for (int g = 0; g * 4 < NKR; ++g) {
             mbar_wait(full + g, ph);
             tc_fence_after();
-            if (g == 0) trace_stamp(p.trace, step, 1);
+            if (g == 0) trace_stamp(p.trace, p.T, step, 2);
             const int c0 = g * 4, c1 = min(NKR, c0 + 4);
-            if (c1 == NKR) trace_stamp(p.trace, step, 2);
+            if (c1 == NKR) trace_stamp(p.trace, p.T, step, 3);
             for (int c = c0; c < c1; ++c) {
               const uint64_t ad = a_base + (uint64_t)c * a_step, bd = b_base + (uint64_t)c * b_step;
               mma_f16(0u, ad, bd, idesc, c > 0);
@@ -957,6 +1086,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
             }
           }
           mma_commit(accum_bar);
+          trace_stamp(p.trace, p.T, step, 4);
           ph ^= 1;
         }
       }
@@ -971,8 +1101,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
       for (int step = 1; step < T; ++step) {
         for (int c = 0; c < NK; ++c) {
           mbar_wait(&full[s], ph);
-          if (c == 0) trace_stamp(p.trace, step, 1);
-          if (c == NK - 1) trace_stamp(p.trace, step, 2);
+          if (c == 0) trace_stamp(p.trace, p.T, step, 1);
+          if (c == NK - 1) trace_stamp(p.trace, p.T, step, 2);
           tc_fence_after();
           const uint64_t ad = a_base + (uint64_t)s * stage_step, bd = b_base + (uint64_t)s * stage_step;
           mma_tf32(0u, ad, bd, idesc, c > 0);
@@ -990,13 +1120,10 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
     const int e = threadIdx.x - 64;
     const int ul = lane & 15, half = lane >> 4;
     uint32_t acc_phase = 0, part_phase = 0;
-    const uint32_t part_local = smem_u32(part);
-    uint32_t part_remote[4], bar_remote[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      part_remote[r] = mapa_u32(part_local, (uint32_t)r);
-      bar_remote[r] = mapa_u32(smem_u32(part_bar), (uint32_t)r);
-    }
+    // destination of this warp's TMEM quarter: CTA q of the cluster, slice ks (= this CTA's rank) of its tile
+    const uint32_t dst_row = mapa_u32(smem_u32(part), (uint32_t)q) + (uint32_t)((ks * UT + ul) * PS * 4);
+    const uint32_t dst_bar = mapa_u32(smem_u32(part_bar), (uint32_t)q);
+    const uint32_t part_tx = (uint32_t)(4 * UT * NB * 4);                // bytes this CTA receives per step
     // resident: s_cur scales what this step writes, s_prev un-scales what this step's MMAs consumed
     const unsigned int* gmax_d = RES ? p.gmax + (size_t)d * (T + 1) : nullptr;
     float s_prev = 1.f, s_cur = 1.f;
@@ -1006,37 +1133,54 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
       const int tp = d == 0 ? t - 1 : t + 1;
       const bool tp_in = tp >= 0 && tp < T;
       float lmax = 0.f;
-      // Saved activations / states / dY of this step do not depend on the recurrence: fetch them into
-      // registers BEFORE waiting for the MMAs so their latency hides behind the tensor-core phase.
-      constexpr int NPF = 4;                              // (unit, batch) pairs per thread that are prefetched
-      const bool prefetch = UT * B <= 128 * NPF;
-      float pg[NPF][4], pa[NPF], pb[NPF], pdy[NPF];
-      if (prefetch) {
+      // Saved activations / states / dY of this step do not depend on the recurrence, and every gate gradient is
+      // linear in dh (LSTM: in dh and dc): fetch them and reduce them to per-pair coefficients BEFORE waiting for
+      // the MMAs, so that global-load and special-function latencies hide behind the tensor-core phase and only
+      // a handful of multiplies remain on the critical path.
+      //   LSTM  k = {o(1-tc^2), tc o(1-o), g i(1-i), c_prev f(1-f), i(1-g^2), f}   tc = tanh(c_t)
+      //   GRU   k = {cn hn r(1-r), (h_prev-n) z(1-z), cn, cn r, z}                  cn = (1-z)(1-n^2)
+      //   tanh  k = {1-h^2}
+      constexpr int NPF = 4;                              // (unit, batch) pairs per thread in one batch
+      const bool single = UT * B <= 128 * NPF;
+      auto load_coefs = [&](int pi, float (&k)[6], float& dyv, bool& valid) {
 #pragma unroll
-        for (int j = 0; j < NPF; ++j) {
-          const int pi = e + 128 * j;
-          pa[j] = pb[j] = pdy[j] = 0.f;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) pg[j][g] = 0.f;
-          if (pi < UT * B) {
-            const int ui = pi % UT, b = pi / UT;
-            if (t < lens_s[b]) {
-              const bool pin = tp_in && (d == 0 || tp < lens_s[b]);
-              const size_t si = (((size_t)d * T + t) * B + b) * H + u0 + ui;
-              const size_t sp = (((size_t)d * T + (tp_in ? tp : 0)) * B + b) * H + u0 + ui;
-              const float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + ui;
-#pragma unroll
-              for (int g = 0; g < G; ++g) pg[j][g] = gp[g * H];
-              pdy[j] = p.dy[((size_t)t * B + b) * H + u0 + ui];
-              if (RNN == DS2_RNN_LSTM) { pa[j] = p.aux[si]; pb[j] = pin ? p.aux[sp] : 0.f; }
-              else if (RNN == DS2_RNN_GRU) { pa[j] = p.aux[si]; pb[j] = pin ? p.hseq[sp] : 0.f; }
-              else pa[j] = p.hseq[si];
-            }
-          }
+        for (int i = 0; i < 6; ++i) k[i] = 0.f;
+        dyv = 0.f;
+        valid = false;
+        if (pi >= UT * B) return;
+        const int ui = pi % UT, b = pi / UT;
+        valid = t < lens_s[b];
+        if (!valid) return;
+        const bool pin = tp_in && (d == 0 || tp < lens_s[b]);
+        const size_t si = (((size_t)d * T + t) * B + b) * H + u0 + ui;
+        const size_t sp = (((size_t)d * T + (tp_in ? tp : 0)) * B + b) * H + u0 + ui;
+        const float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + ui;
+        dyv = p.dy[((size_t)t * B + b) * H + u0 + ui];
+        if (RNN == DS2_RNN_LSTM) {
+          const float gi = gp[0], gf = gp[H], gg = gp[2 * H], go = gp[3 * H];
+          const float c = p.aux[si], c_prev = pin ? p.aux[sp] : 0.f;
+          const float tc = fast_tanh(c);                  // the forward sweep produced h = o * fast_tanh(c)
+          k[0] = go * (1.f - tc * tc); k[1] = tc * go * (1.f - go); k[2] = gg * gi * (1.f - gi);
+          k[3] = c_prev * gf * (1.f - gf); k[4] = gi * (1.f - gg * gg); k[5] = gf;
+        } else if (RNN == DS2_RNN_GRU) {
+          const float r = gp[0], z = gp[H], n = gp[2 * H];
+          const float hn = p.aux[si], h_prev = pin ? p.hseq[sp] : 0.f;
+          const float cn = (1.f - z) * (1.f - n * n);
+          k[0] = cn * hn * r * (1.f - r); k[1] = (h_prev - n) * z * (1.f - z); k[2] = cn; k[3] = cn * r; k[4] = z;
+        } else {
+          const float hv = p.hseq[si];
+          k[0] = 1.f - hv * hv;
         }
+      };
+      float kc[NPF][6], pdy[NPF];
+      bool pvalid[NPF];
+      if (single) {
+#pragma unroll
+        for (int j = 0; j < NPF; ++j) load_coefs(e + 128 * j, kc[j], pdy[j], pvalid[j]);
       }
       if (step > 0) {
-        // publish this CTA's partial tile: row (16q + ul), 32 columns split over the two half-warps
+        if (e == 0) mbar_arrive_expect_tx(part_bar, part_tx);   // arm this step's phase (peers may already have sent)
+        // send this CTA's partial tile: row (16q + ul), 32 columns split over the two half-warps
         mbar_wait(accum_bar, acc_phase);
         tc_fence_after();
         if (RES) {
@@ -1044,100 +1188,110 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
           s_prev = s_cur;
           s_cur = pow2_scale_for(__uint_as_float(ld_acquire(gmax_d + step)), s_prev);
         }
-        if (e == 0) trace_stamp(p.trace, step, 3);
+        if (e == 0) trace_stamp(p.trace, p.T, step, 5);
         for (int cb = 0; cb < NB; cb += 32) {
           float acc[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, acc);
+          float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float hi = __shfl_sync(0xffffffffu, acc[16 + j], ul);
-            const float v = half ? hi : acc[j];
-            const int b = cb + half * 16 + j;
-            if (b < B) part[(q * 16 + ul) * NBp + b] = v;
+            v[j] = half ? hi : acc[j];
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c0 = cb + half * 16 + 4 * i;        // NB is a multiple of 8: a group of 4 columns is in or out
+            if (c0 < NB) st_async_v4(dst_row + (uint32_t)(c0 * 4), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], dst_bar);
           }
         }
         acc_phase ^= 1;
         tc_fence_before();
-        named_bar_sync(1, 128);
-        if (e < 4) mbar_arrive_remote(bar_remote[e]);     // release.cluster: the tile is visible to the peer
-        mbar_wait_cluster(part_bar, part_phase);          // all four partial tiles are published
+        if (e == 0) trace_stamp(p.trace, p.T, step, 6);
+        mbar_wait_cluster(part_bar, part_phase, p.err);   // all four slices of this CTA's units have landed
         part_phase ^= 1;
       }
-      if (e == 0) trace_stamp(p.trace, step, 4);
+      if (e == 0) trace_stamp(p.trace, p.T, step, 7);
       const float inv_prev = 1.f / s_prev;
-      // one (unit, batch) pair: recurrent term from the four partial tiles, gate backward, stores
-      auto finish_pair = [&](int pi, float g0, float g1, float g2, float g3, float a_si, float a_prev, float dyv) {
-        const int ui = pi % UT, b = pi / UT;
-        const bool valid = t < lens_s[b];
-        const size_t si = (((size_t)d * T + t) * B + b) * H + u0 + ui;
-        float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + ui;
-        __half* hp16 = RES ? p.dg16 + (((size_t)t * B + b) * D + d) * GH + u0 + ui : nullptr;
-        if (!valid) {
-#pragma unroll
-          for (int g = 0; g < G; ++g) gp[g * H] = 0.f;
-          if (RNN == DS2_RNN_GRU) p.aux[si] = 0.f;
-          if (RES) {
-#pragma unroll
-            for (int g = 0; g < G; ++g) hp16[g * H] = __float2half_rn(0.f);
-          }
-          return;
-        }
-        float dh = dyv;
-        if (step > 0) {
-          const uint32_t off = (uint32_t)(((ks * UT + ui) * NBp + b) * 4);
-          const float rec = (ld_dsmem(part_remote[0] + off) + ld_dsmem(part_remote[1] + off)) +
-                            (ld_dsmem(part_remote[2] + off) + ld_dsmem(part_remote[3] + off));
-          dh += RES ? rec * inv_prev : rec;
-        }
-        if (RNN == DS2_RNN_LSTM) {
-          LstmBwd r = lstm_cell_bwd(g0, g1, g2, g3, a_si, a_prev, dh, cst[ui * NBp + b]);
-          gp[0] = r.di; gp[H] = r.df; gp[2 * H] = r.dg; gp[3 * H] = r.d_o;
-          cst[ui * NBp + b] = r.dc_prev;
-          if (RES) {
-            lmax = fmaxf(lmax, fmaxf(fmaxf(fabsf(r.di), fabsf(r.df)), fmaxf(fabsf(r.dg), fabsf(r.d_o))));
-            hp16[0] = to_half_sat(r.di * s_cur); hp16[H] = to_half_sat(r.df * s_cur);
-            hp16[2 * H] = to_half_sat(r.dg * s_cur); hp16[3 * H] = to_half_sat(r.d_o * s_cur);
-          }
-        } else if (RNN == DS2_RNN_GRU) {
-          dh += cst[ui * NBp + b];
-          GruBwd r = gru_cell_bwd(g0, g1, g2, a_si, a_prev, dh);
-          gp[0] = r.dr; gp[H] = r.dz; gp[2 * H] = r.dxn;
-          p.aux[si] = r.dhn;
-          cst[ui * NBp + b] = r.dh_prev;
-          if (RES) {
-            lmax = fmaxf(lmax, fmaxf(fabsf(r.dr), fmaxf(fabsf(r.dz), fabsf(r.dhn))));
-            hp16[0] = to_half_sat(r.dr * s_cur); hp16[H] = to_half_sat(r.dz * s_cur);
-            hp16[2 * H] = to_half_sat(r.dhn * s_cur);       // the h-side n-gate gradient (dGh_n)
-          }
-        } else {
-          const float dgv = dh * (1.f - a_si * a_si);
-          gp[0] = dgv;
-          if (RES) { lmax = fmaxf(lmax, fabsf(dgv)); hp16[0] = to_half_sat(dgv * s_cur); }
-        }
-      };
-      if (prefetch) {
+      // A batch of pairs: recurrent term from the four partial tiles (all remote loads issued first), gate
+      // backward from the coefficients.  The scaled fp16 copy (resident variant: the next step's MMA operand) is
+      // stored here; the fp32 gate gradients, which only the weight-gradient GEMMs after the sweep read, are
+      // returned in o[] (o[4]: GRU dGh_n) for store_dg().
+      auto finish4 = [&](int base, const float (&k)[NPF][6], const float (&dyv)[NPF], const bool (&valid)[NPF],
+                         float (&o)[NPF][5]) {
+        float r4[NPF][4];
 #pragma unroll
         for (int j = 0; j < NPF; ++j) {
-          const int pi = e + 128 * j;
-          if (pi < UT * B) finish_pair(pi, pg[j][0], pg[j][1], pg[j][2], pg[j][3], pa[j], pb[j], pdy[j]);
+          const int pi = base + 128 * j;
+          const bool ld = step > 0 && valid[j];
+          const int off = ld ? (pi % UT) * PS + pi / UT : 0;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) r4[j][r] = ld ? part[r * UT * PS + off] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < NPF; ++j) {
+          const int pi = base + 128 * j;
+          o[j][0] = o[j][1] = o[j][2] = o[j][3] = o[j][4] = 0.f;
+          if (pi >= UT * B) continue;
+          const int ui = pi % UT, b = pi / UT, ci = ui * NBp + b;
+          __half* hp16 = RES ? p.dg16 + (((size_t)t * B + b) * D + d) * GH + u0 + ui : nullptr;
+          if (!valid[j]) {
+            if (RES) {
+#pragma unroll
+              for (int g = 0; g < G; ++g) hp16[g * H] = __float2half_rn(0.f);
+            }
+            continue;
+          }
+          const float rec = (r4[j][0] + r4[j][1]) + (r4[j][2] + r4[j][3]);
+          float dh = dyv[j] + (RES ? rec * inv_prev : rec);
+          if (RNN == DS2_RNN_LSTM) {
+            const float dc = fmaf(dh, k[j][0], cst[ci]);
+            o[j][0] = dc * k[j][2]; o[j][1] = dc * k[j][3]; o[j][2] = dc * k[j][4]; o[j][3] = dh * k[j][1];
+            cst[ci] = dc * k[j][5];
+            if (RES) {
+              lmax = fmaxf(lmax, fmaxf(fmaxf(fabsf(o[j][0]), fabsf(o[j][1])), fmaxf(fabsf(o[j][2]), fabsf(o[j][3]))));
+#pragma unroll
+              for (int g = 0; g < 4; ++g) hp16[g * H] = to_half_sat(o[j][g] * s_cur);
+            }
+          } else if (RNN == DS2_RNN_GRU) {
+            dh += cst[ci];
+            o[j][0] = dh * k[j][0]; o[j][1] = dh * k[j][1]; o[j][2] = dh * k[j][2]; o[j][4] = dh * k[j][3];
+            cst[ci] = dh * k[j][4];
+            if (RES) {
+              lmax = fmaxf(lmax, fmaxf(fabsf(o[j][0]), fmaxf(fabsf(o[j][1]), fabsf(o[j][4]))));
+              hp16[0] = to_half_sat(o[j][0] * s_cur); hp16[H] = to_half_sat(o[j][1] * s_cur);
+              hp16[2 * H] = to_half_sat(o[j][4] * s_cur);     // the h-side n-gate gradient (dGh_n)
+            }
+          } else {
+            o[j][0] = dh * k[j][0];
+            if (RES) { lmax = fmaxf(lmax, fabsf(o[j][0])); hp16[0] = to_half_sat(o[j][0] * s_cur); }
+          }
+        }
+      };
+      auto store_dg = [&](int pi, const float (&o)[5]) {
+        const int ui = pi % UT, b = pi / UT;
+        float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + ui;
+#pragma unroll
+        for (int g = 0; g < G; ++g) gp[g * H] = o[g];
+        if (RNN == DS2_RNN_GRU) p.aux[(((size_t)d * T + t) * B + b) * H + u0 + ui] = o[4];
+      };
+      // the non-resident variants stream the fp32 gate gradients themselves: nothing can be deferred there
+      const bool defer = RES && p.defer && single;
+      float sv[NPF][5];
+      if (single) {
+        finish4(e, kc, pdy, pvalid, sv);
+        if (!defer) {
+#pragma unroll
+          for (int j = 0; j < NPF; ++j)
+            if (e + 128 * j < UT * B) store_dg(e + 128 * j, sv[j]);
         }
       } else {
-        for (int pi = e; pi < UT * B; pi += 128) {
-          const int ui = pi % UT, b = pi / UT;
-          float g4[4] = {0.f, 0.f, 0.f, 0.f}, a_si = 0.f, a_prev = 0.f, dyv = 0.f;
-          if (t < lens_s[b]) {
-            const bool pin = tp_in && (d == 0 || tp < lens_s[b]);
-            const size_t si = (((size_t)d * T + t) * B + b) * H + u0 + ui;
-            const size_t sp = (((size_t)d * T + (tp_in ? tp : 0)) * B + b) * H + u0 + ui;
-            const float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + ui;
+        for (int base = e; base < UT * B; base += 128 * NPF) {
 #pragma unroll
-            for (int g = 0; g < G; ++g) g4[g] = gp[g * H];
-            dyv = p.dy[((size_t)t * B + b) * H + u0 + ui];
-            if (RNN == DS2_RNN_LSTM) { a_si = p.aux[si]; a_prev = pin ? p.aux[sp] : 0.f; }
-            else if (RNN == DS2_RNN_GRU) { a_si = p.aux[si]; a_prev = pin ? p.hseq[sp] : 0.f; }
-            else a_si = p.hseq[si];
-          }
-          finish_pair(pi, g4[0], g4[1], g4[2], g4[3], a_si, a_prev, dyv);
+          for (int j = 0; j < NPF; ++j) load_coefs(base + 128 * j, kc[j], pdy[j], pvalid[j]);
+          finish4(base, kc, pdy, pvalid, sv);
+#pragma unroll
+          for (int j = 0; j < NPF; ++j)
+            if (base + 128 * j < UT * B) store_dg(base + 128 * j, sv[j]);
         }
       }
       if (RES) {
@@ -1145,15 +1299,27 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
         for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
         if (lane == 0) atomicMax(cta_max, __float_as_uint(lmax));     // non-negative floats order like uints
       }
+      if (e == 0) trace_stamp(p.trace, p.T, step, 8);
       named_bar_sync(1, 128);
       if (e == 0) {
+        trace_stamp(p.trace, p.T, step, 9);
         if (RES) {
           atomicMax(p.gmax + (size_t)d * (T + 1) + step + 1, cta_max[0]);
           cta_max[0] = 0u;
         }
-        fence_proxy_async_all();
+        fence_proxy_async_global();
+        trace_stamp(p.trace, p.T, step, 10);
         red_release(ctr, 1u);
-        trace_stamp(p.trace, step, 5);
+        trace_stamp(p.trace, p.T, step, 11);
+        trace_stamp_ns(p.trace, p.T, step, 12);
+      }
+      if (defer) {
+#pragma unroll
+        for (int j = 0; j < NPF; ++j) {
+          const int pi = e + 128 * j;
+          if (pi < UT * B) store_dg(pi, sv[j]);
+        }
+        if (e == 0) trace_stamp(p.trace, p.T, step, 13);
       }
     }
   }
@@ -1166,7 +1332,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
 static size_t splitk_smem_bytes(int NB) {
   using namespace rp;
   size_t NBp = NB + 1;
-  return 1024 + (size_t)STAGES * (A_BYTES + (size_t)NB * 128) + ((64 + UT) * NBp + NB + 8) * sizeof(float) +
+  size_t PS = ((NB + 3) & ~3) + 4;
+  return 1024 + (size_t)STAGES * (A_BYTES + (size_t)NB * 128) + (64 * PS + UT * NBp + NB + 8) * sizeof(float) +
          (2 * STAGES + 3) * sizeof(uint64_t) + 64;
 }
 
@@ -1183,7 +1350,8 @@ __global__ void absmax_kernel(size_t n, const float* __restrict__ x, unsigned in
 static size_t splitk_res_smem_bytes(int NB, int Kc) {
   using namespace rp;
   size_t NBp = NB + 1;
-  return 1024 + (size_t)(Kc / 64) * (A_BYTES + (size_t)NB * 128) + ((64 + UT) * NBp + NB + 8) * sizeof(float) +
+  size_t PS = ((NB + 3) & ~3) + 4;
+  return 1024 + (size_t)(Kc / 64) * (A_BYTES + (size_t)NB * 128) + (64 * PS + UT * NBp + NB + 8) * sizeof(float) +
          (32 + STAGES + 3) * sizeof(uint64_t) + 64;
 }
 // workspace of the resident backward: [4 KB control][gmax D*(T+1) uints][W^T fp16: D*H*GH][dg16: T*B*D*GH]
@@ -1205,6 +1373,7 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
   p.training = 1;
   p.len = a.len; p.gates = a.gates; p.hseq = a.hseq; p.aux = a.aux; p.dy = a.dy;
   p.trace = trace_ptr_from_env("DS2_TRACE_BWD");
+  p.defer = sweep_defer_default();
   set_acc_layout(p);
   char* base = static_cast<char*>(ws);
   p.err = reinterpret_cast<int*>(base);
