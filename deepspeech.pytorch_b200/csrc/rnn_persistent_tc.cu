@@ -44,6 +44,8 @@ struct PersistParams {
   CUtensorMap tmW[2];   // 3-D (k, unit, gate) over W_hh[d]
   CUtensorMap tmV[2];   // 2-D (k, row) over the per-direction vector sequence (hseq[d] as [T*B, H])
   CUtensorMap tmV2[2];  // bwd GRU: the n-gate part of dGh lives in the aux buffer
+  CUtensorMap tmV3[2];  // resident: 3-D view (k in chunk, row, chunk) of the streamed fp16 operand, box = 4 chunks
+  int box3;             // 1: tmV3 is valid (number of chunks divisible by 4): one TMA instruction per group
   int T, B, NB, H, D, NT, G, training;
   const float* dy;      // bwd: (T,B,H)
   __half* h16;          // resident fwd: fp16 copy of hseq (D,T,B,H), the MMA operand of the next step
@@ -154,6 +156,13 @@ __device__ __forceinline__ void trace_stamp_ns(long long* trace, int T, int step
   }
 }
 
+// Resident variants: the streamed operand arrives in groups of 4 K chunks (256 k), one mbarrier per group.
+// (A single-chunk first group was measured: the MMA chain starts ~250 cycles earlier but the extra
+// producer instructions delay the later groups by as much; what limits the start of a step is the ~110
+// cycles the single producer thread needs per TMA instruction, hence one 3-D box per group where possible.)
+__device__ __forceinline__ int grp_begin(int g) { return 4 * g; }
+__device__ __forceinline__ int grp_count(int nkr) { return (nkr + 3) / 4; }
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -174,6 +183,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
   const int B_BYTES = NB * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   const int NBp = NB + 1;
   const int NKR = H / 64;                                  // resident: 64 fp16 (128 B) of K per chunk
+  const int NG = grp_count(NKR);
   // streaming layout: STAGES x (A | B) ; resident layout: NKR x A (weights) then NKR x B (h chunks)
   const int ring_bytes = RES ? NKR * STAGE_BYTES : STAGES * STAGE_BYTES;
   float* ex = reinterpret_cast<float*>(smem + ring_bytes);            // [4][UT][NBp]
@@ -231,11 +241,16 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
           grid_wait_counter(ctr, (unsigned int)p.NT * (unsigned int)step, p.err);
           fence_proxy_async_global();
           trace_stamp(p.trace, p.T, step, 0);
-          for (int g = 0; g * 4 < NKR; ++g) {  // one mbarrier per group of 4 chunks (256 k)
+          for (int g = 0; g < NG; ++g) {  // one mbarrier per group of chunks
             uint64_t* fb = full + g;
-            const int c0 = g * 4, c1 = min(NKR, c0 + 4);
-            mbar_arrive_expect_tx(fb, (uint32_t)((c1 - c0) * B * 128));
-            for (int c = c0; c < c1; ++c) tma_load_2d(hbuf + c * B_BYTES, &p.tmV[d], fb, c * 64, tp * B);
+            const int c0 = grp_begin(g), c1 = min(NKR, grp_begin(g + 1));
+            if (p.box3) {
+              mbar_arrive_expect_tx(fb, (uint32_t)(4 * B_BYTES));
+              tma_load_3d(hbuf + c0 * B_BYTES, &p.tmV3[d], fb, 0, tp * B, c0);
+            } else {
+              mbar_arrive_expect_tx(fb, (uint32_t)((c1 - c0) * B * 128));
+              for (int c = c0; c < c1; ++c) tma_load_2d(hbuf + c * B_BYTES, &p.tmV[d], fb, c * 64, tp * B);
+            }
           }
           trace_stamp(p.trace, p.T, step, 1);
         }
@@ -273,11 +288,11 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
         mbar_wait(&empty[0], 0);                 // weights resident
         uint32_t ph = 0;
         for (int step = 1; step < T; ++step) {
-          for (int g = 0; g * 4 < NKR; ++g) {
+          for (int g = 0; g < NG; ++g) {
             mbar_wait(full + g, ph);
             tc_fence_after();
             if (g == 0) trace_stamp(p.trace, p.T, step, 2);
-            const int c0 = g * 4, c1 = min(NKR, c0 + 4);
+            const int c0 = grp_begin(g), c1 = min(NKR, grp_begin(g + 1));
             if (c1 == NKR) trace_stamp(p.trace, p.T, step, 3);
             for (int c = c0; c < c1; ++c) {
               const uint64_t ad = a_base + (uint64_t)c * a_step, bd = b_base + (uint64_t)c * b_step;
@@ -393,41 +408,38 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
       if (e == 0) trace_stamp(p.trace, p.T, step, 6);
       named_bar_sync(1, 128);
       if (e == 0) trace_stamp(p.trace, p.T, step, 7);
-      // ---------------- combine: (unit, batch) pairs over the 128 epilogue threads, four pairs per thread at a
-      // time and stage by stage (independent special-function chains).  Only the fp16 copy of h_t (resident
-      // variant) is read by the next step; the fp32 outputs (sequence output, saved activations / cell state for
-      // the backward) are returned in o[] so that the caller can store them after the barrier arrival.
+      // ---------------- combine: thread e owns the 4 consecutive units 4*(e&3)..+3 of batch column (e>>2) [+32
+      // per block], so every global access is one 8- or 16-byte vector, and the four cells are processed stage by
+      // stage (independent special-function chains).  Only the fp16 copy of h_t (resident variant) is read by
+      // the next step; the fp32 outputs (sequence output, saved activations / cell state for the backward) are
+      // returned in o[] so that the caller can store them after the barrier arrival.
       constexpr int NDF = 4;
-      auto combine4 = [&](int base, float (&o)[NDF][6]) {
+      const int uq = 4 * (e & 3);                  // first of this thread's units inside the CTA's 16
+      auto combine4 = [&](int b, float (&o)[6][NDF]) {
         float e0[NDF], e1[NDF], e2[NDF], e3[NDF], cp[NDF], hval[NDF];
-        int ci[NDF];
-        bool in[NDF], valid[NDF];
+        const bool valid = t < lens_s[b];
 #pragma unroll
         for (int j = 0; j < NDF; ++j) {
-          const int pi = base + 128 * j;
-          in[j] = pi < UT * B;
-          const int ui = in[j] ? pi % UT : 0, b = in[j] ? pi / UT : 0;
-          valid[j] = in[j] && t < lens_s[b];
-          ci[j] = ui * NBp + b;
+          const int ui = uq + j;
           e0[j] = ex[(0 * UT + ui) * NBp + b]; e1[j] = ex[(1 * UT + ui) * NBp + b];
           e2[j] = ex[(2 * UT + ui) * NBp + b]; e3[j] = ex[(3 * UT + ui) * NBp + b];
-          cp[j] = cst[ci[j]];
+          cp[j] = cst[ui * NBp + b];
         }
         if (RNN == DS2_RNN_LSTM) {
           float cval[NDF], th[NDF];
 #pragma unroll
-          for (int j = 0; j < NDF; ++j) cval[j] = valid[j] ? fmaf(e1[j], cp[j], e0[j] * e2[j]) : 0.f;
+          for (int j = 0; j < NDF; ++j) cval[j] = valid ? fmaf(e1[j], cp[j], e0[j] * e2[j]) : 0.f;
 #pragma unroll
           for (int j = 0; j < NDF; ++j) th[j] = ex2_ftz(-2.f * LOG2E * cval[j]);
 #pragma unroll
           for (int j = 0; j < NDF; ++j) th[j] = rcp_ftz(1.f + th[j]);
 #pragma unroll
           for (int j = 0; j < NDF; ++j) {
-            hval[j] = valid[j] ? e3[j] * fmaf(2.f, th[j], -1.f) : 0.f;
-            if (valid[j]) cst[ci[j]] = cval[j];
-            o[j][0] = valid[j] ? e0[j] : 0.f; o[j][1] = valid[j] ? e1[j] : 0.f;
-            o[j][2] = valid[j] ? e2[j] : 0.f; o[j][3] = valid[j] ? e3[j] : 0.f;
-            o[j][4] = cval[j];
+            hval[j] = valid ? e3[j] * fmaf(2.f, th[j], -1.f) : 0.f;
+            if (valid) cst[(uq + j) * NBp + b] = cval[j];
+            o[0][j] = valid ? e0[j] : 0.f; o[1][j] = valid ? e1[j] : 0.f;
+            o[2][j] = valid ? e2[j] : 0.f; o[3][j] = valid ? e3[j] : 0.f;
+            o[4][j] = cval[j];
           }
         } else if (RNN == DS2_RNN_GRU) {
           float th[NDF];
@@ -437,49 +449,51 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
           for (int j = 0; j < NDF; ++j) th[j] = rcp_ftz(1.f + th[j]);
 #pragma unroll
           for (int j = 0; j < NDF; ++j) {
-            const float nval = valid[j] ? fmaf(2.f, th[j], -1.f) : 0.f;
-            hval[j] = valid[j] ? fmaf(e1[j], cp[j] - nval, nval) : 0.f;
-            if (valid[j]) cst[ci[j]] = hval[j];
-            o[j][0] = valid[j] ? e0[j] : 0.f; o[j][1] = valid[j] ? e1[j] : 0.f; o[j][2] = nval; o[j][3] = 0.f;
-            o[j][4] = valid[j] ? e2[j] : 0.f;
+            const float nval = valid ? fmaf(2.f, th[j], -1.f) : 0.f;
+            hval[j] = valid ? fmaf(e1[j], cp[j] - nval, nval) : 0.f;
+            if (valid) cst[(uq + j) * NBp + b] = hval[j];
+            o[0][j] = valid ? e0[j] : 0.f; o[1][j] = valid ? e1[j] : 0.f; o[2][j] = nval; o[3][j] = 0.f;
+            o[4][j] = valid ? e2[j] : 0.f;
           }
         } else {
 #pragma unroll
           for (int j = 0; j < NDF; ++j) {
-            hval[j] = valid[j] ? e0[j] : 0.f;
-            o[j][0] = hval[j]; o[j][1] = o[j][2] = o[j][3] = o[j][4] = 0.f;
+            hval[j] = valid ? e0[j] : 0.f;
+            o[0][j] = hval[j]; o[1][j] = o[2][j] = o[3][j] = o[4][j] = 0.f;
           }
         }
 #pragma unroll
-        for (int j = 0; j < NDF; ++j) {
-          o[j][5] = hval[j];
-          if (RES && in[j]) {
-            const int pi = base + 128 * j;
-            p.h16[(((size_t)d * T + t) * B + pi / UT) * H + u0 + pi % UT] = __float2half_rn(hval[j]);
-          }
+        for (int j = 0; j < NDF; ++j) o[5][j] = hval[j];
+        if (RES) {
+          const __half2 lo = __floats2half2_rn(hval[0], hval[1]), hi = __floats2half2_rn(hval[2], hval[3]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const unsigned int*>(&lo);
+          pk.y = *reinterpret_cast<const unsigned int*>(&hi);
+          *reinterpret_cast<uint2*>(p.h16 + (((size_t)d * T + t) * B + b) * H + u0 + uq) = pk;
         }
       };
-      auto store_pair = [&](int pi, const float (&o)[6]) {
-        const int ui = pi % UT, b = pi / UT;
-        const size_t so = (((size_t)d * T + t) * B + b) * H + u0 + ui;
-        float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + ui;
-        if (RNN != DS2_RNN_TANH) p.aux[so] = o[4];
+      auto st4 = [](float* dst, const float (&v)[NDF]) {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      };
+      auto store4 = [&](int b, const float (&o)[6][NDF]) {
+        const size_t so = (((size_t)d * T + t) * B + b) * H + u0 + uq;
+        float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + uq;
+        if (RNN != DS2_RNN_TANH) st4(p.aux + so, o[4]);
         if (p.training) {
 #pragma unroll
-          for (int g = 0; g < G; ++g) gp[g * H] = o[g];
+          for (int g = 0; g < G; ++g) st4(gp + g * H, o[g]);
         }
-        p.hseq[so] = o[5];
+        st4(p.hseq + so, o[5]);
       };
-      const bool defer = RES && p.defer && UT * B <= 128 * NDF;
-      float sv[NDF][6];
+      const bool defer = RES && p.defer && B <= 32;
+      const int b_own = e >> 2;
+      float sv[6][NDF];
       if (defer) {
-        combine4(e, sv);
+        if (b_own < B) combine4(b_own, sv);
       } else {
-        for (int base = e; base < UT * B; base += 128 * NDF) {
-          combine4(base, sv);
-#pragma unroll
-          for (int j = 0; j < NDF; ++j)
-            if (base + 128 * j < UT * B) store_pair(base + 128 * j, sv[j]);
+        for (int b = b_own; b < B; b += 32) {
+          combine4(b, sv);
+          store4(b, sv);
         }
       }
       if (e == 0) trace_stamp(p.trace, p.T, step, 8);
@@ -494,11 +508,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
         trace_stamp_ns(p.trace, p.T, step, 12);
       }
       if (defer) {
-#pragma unroll
-        for (int j = 0; j < NDF; ++j) {
-          const int pi = e + 128 * j;
-          if (pi < UT * B) store_pair(pi, sv[j]);
-        }
+        if (b_own < B) store4(b_own, sv);
         if (e == 0) trace_stamp(p.trace, p.T, step, 13);
       }
     }
@@ -521,6 +531,11 @@ static long long* trace_ptr_from_env(const char* name) {
   return e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 10)) : nullptr;
 }
 
+// the epilogues use 8- / 16-byte vector accesses on these buffers
+static bool vec_ok(const void* a, const void* b = nullptr, const void* c = nullptr, const void* d = nullptr) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+           reinterpret_cast<uintptr_t>(d)) & 15) == 0;
+}
 static int env_flag(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -555,7 +570,7 @@ static void set_acc_layout(PersistParams& p) {
 static bool fwd_eligible(const SeqArgs& a) {
   if (a.h0 || a.c0) return false;                 // initial states -> generic step kernels
   if (a.H % 32 != 0 || a.B > 256 || a.T < 2) return false;
-  return true;
+  return vec_ok(a.gates, a.hseq, a.aux);
 }
 
 __global__ void f32_to_f16_kernel(size_t n, const float* __restrict__ in, __half* __restrict__ out) {
@@ -580,6 +595,7 @@ static int launch_fwd_resident(const SeqArgs& a, void* ws, size_t ws_bytes, cuda
   using namespace rp;
   const int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
   if (a.H % 64 != 0 || a.H / 64 > 32) return 1;
+  if (!vec_ok(a.gates, a.hseq, a.aux)) return 1;
   if (ws_bytes < res_ws_bytes(G, a.T, a.B, a.H, a.D)) return 1;
   PersistParams p{};
   p.T = a.T; p.B = a.B; p.NB = (a.B + 7) / 8 * 8; p.H = a.H; p.D = a.D; p.NT = a.H / UT; p.G = G;
@@ -622,6 +638,12 @@ static int launch_fwd_resident(const SeqArgs& a, void* ws, size_t ws_bytes, cuda
     if (rc) return rc;
     rc = make_tmap_f16(&p.tmV[d], p.h16 + (size_t)d * a.T * a.B * a.H, 2, a.H, a.T * a.B, 1, (size_t)a.H, 0, 64, a.B, 1);
     if (rc) return rc;
+    p.box3 = (a.H / 64) % 4 == 0;
+    if (p.box3) {   // rows b >= B of a box belong to the next time step (or are zero-filled): those N columns are discarded
+      rc = make_tmap_f16(&p.tmV3[d], p.h16 + (size_t)d * a.T * a.B * a.H, 3, 64, a.T * a.B, a.H / 64, (size_t)a.H, 64, 64,
+                         p.NB, 4);
+      if (rc) return rc;
+    }
   }
   DS2_CHECK_CUDA(cudaMemsetAsync(ws, 0, 4096, st));
   for (int li = 0; li < launches; ++li) {
@@ -943,13 +965,14 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ __half to_half_sat(float v) {
   return __float2half_rn(fminf(fmaxf(v, -65000.f), 65000.f));
 }
-__device__ __forceinline__ float pow2_scale_for(float m, float s_prev) {
-  if (!(m > 0.f)) return s_prev;
-  int ex;
-  frexpf(m, &ex);                       // m = f * 2^ex, f in [0.5, 1)
-  ex = max(-100, min(100, 8 - ex));
-  return ldexpf(1.f, ex);
+// scale exponent for a step whose maximum magnitude is m: m * 2^sx lands in [2^7, 2^8).  Exponent arithmetic on
+// the float bits (m = f * 2^(E-126), f in [0.5, 1)) instead of frexpf / ldexpf / a division on the critical path.
+__device__ __forceinline__ int pow2_exp_for(unsigned int m_bits, int sx_prev) {
+  if (m_bits == 0u || m_bits >= 0x7f800000u) return sx_prev;     // 0, inf, nan: keep the previous scale
+  const int E = (int)((m_bits >> 23) & 0xffu);
+  return max(-100, min(100, 134 - E));
 }
+__device__ __forceinline__ float pow2f(int ex) { return __int_as_float((ex + 127) << 23); }   // |ex| <= 100
 
 template <int RNN, bool RES>
 __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __grid_constant__ PersistParams p) {
@@ -963,6 +986,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
   const int B_BYTES = NB * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   const int NBp = NB + 1;
   const int NKR = (G * H / 4) / 64;                                      // resident: 64 fp16 of K per chunk
+  const int NG = grp_count(NKR);
   const int ring_bytes = RES ? NKR * STAGE_BYTES : STAGES * STAGE_BYTES;
   const int PS = ((NB + 3) & ~3) + 4;                                    // row pitch of the received tiles (16 B aligned)
   float* part = reinterpret_cast<float*>(smem + ring_bytes);             // [4 sources][16][PS] partial dh_rec
@@ -1026,12 +1050,23 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
           grid_wait_counter(ctr, n_arrive * (unsigned int)step, p.err);
           fence_proxy_async_global();
           trace_stamp(p.trace, p.T, step, 0);
-          for (int g = 0; g * 4 < NKR; ++g) {
+          // every CTA's atomicMax of the previous step precedes its arrival: the maximum is final.  It is handed
+          // to the epilogue warps through shared memory (published before the last group is armed, so the
+          // full-barrier -> MMA -> accumulator-barrier chain orders it) instead of a ~300-cycle global load
+          // on their critical path.
+          const unsigned int gm = ld_relaxed(p.gmax + (size_t)d * (T + 1) + step);
+          for (int g = 0; g < NG; ++g) {
             uint64_t* fb = full + g;
-            const int c0 = g * 4, c1 = min(NKR, c0 + 4);
-            mbar_arrive_expect_tx(fb, (uint32_t)((c1 - c0) * B * 128));
-            for (int c = c0; c < c1; ++c)
-              tma_load_2d(vbuf + c * B_BYTES, &p.tmV[d], fb, d * GH + kbase + c * 64, tn * B);
+            const int c0 = grp_begin(g), c1 = min(NKR, grp_begin(g + 1));
+            if (c1 == NKR) *(volatile unsigned int*)(cta_max + 1) = gm;
+            if (p.box3) {
+              mbar_arrive_expect_tx(fb, (uint32_t)(4 * B_BYTES));
+              tma_load_3d(vbuf + c0 * B_BYTES, &p.tmV3[d], fb, 0, tn * B, (d * GH + kbase) / 64 + c0);
+            } else {
+              mbar_arrive_expect_tx(fb, (uint32_t)((c1 - c0) * B * 128));
+              for (int c = c0; c < c1; ++c)
+                tma_load_2d(vbuf + c * B_BYTES, &p.tmV[d], fb, d * GH + kbase + c * 64, tn * B);
+            }
           }
           trace_stamp(p.trace, p.T, step, 1);
         }
@@ -1071,11 +1106,11 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
         mbar_wait(&empty[0], 0);
         uint32_t ph = 0;
         for (int step = 1; step < T; ++step) {
-          for (int g = 0; g * 4 < NKR; ++g) {
+          for (int g = 0; g < NG; ++g) {
             mbar_wait(full + g, ph);
             tc_fence_after();
             if (g == 0) trace_stamp(p.trace, p.T, step, 2);
-            const int c0 = g * 4, c1 = min(NKR, c0 + 4);
+            const int c0 = grp_begin(g), c1 = min(NKR, grp_begin(g + 1));
             if (c1 == NKR) trace_stamp(p.trace, p.T, step, 3);
             for (int c = c0; c < c1; ++c) {
               const uint64_t ad = a_base + (uint64_t)c * a_step, bd = b_base + (uint64_t)c * b_step;
@@ -1126,8 +1161,9 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
     const uint32_t part_tx = (uint32_t)(4 * UT * NB * 4);                // bytes this CTA receives per step
     // resident: s_cur scales what this step writes, s_prev un-scales what this step's MMAs consumed
     const unsigned int* gmax_d = RES ? p.gmax + (size_t)d * (T + 1) : nullptr;
-    float s_prev = 1.f, s_cur = 1.f;
-    if (RES) s_cur = pow2_scale_for(__uint_as_float(ld_acquire(gmax_d)), 1.f);
+    int sx_prev = 0, sx_cur = 0;
+    if (RES) sx_cur = pow2_exp_for(ld_acquire(gmax_d), 0);
+    float s_cur = pow2f(sx_cur), inv_prev = 1.f;
     for (int step = 0; step < T; ++step) {
       const int t = d == 0 ? T - 1 - step : step;
       const int tp = d == 0 ? t - 1 : t + 1;
@@ -1140,53 +1176,76 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
       //   LSTM  k = {o(1-tc^2), tc o(1-o), g i(1-i), c_prev f(1-f), i(1-g^2), f}   tc = tanh(c_t)
       //   GRU   k = {cn hn r(1-r), (h_prev-n) z(1-z), cn, cn r, z}                  cn = (1-z)(1-n^2)
       //   tanh  k = {1-h^2}
-      constexpr int NPF = 4;                              // (unit, batch) pairs per thread in one batch
-      const bool single = UT * B <= 128 * NPF;
-      auto load_coefs = [&](int pi, float (&k)[6], float& dyv, bool& valid) {
+      // Thread e owns the 4 consecutive units 4*(e&3)..+3 of batch column (e>>2) [+32 per block]: every global
+      // access is one 8- or 16-byte vector.
+      constexpr int NPF = 4;
+      const bool single = B <= 32;
+      const int uq = 4 * (e & 3), b_own = e >> 2;
+      auto ld4 = [](const float* src, float (&v)[NPF]) {
+        const float4 x = *reinterpret_cast<const float4*>(src);
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+      };
+      auto load_coefs = [&](int b, float (&k)[6][NPF], float (&dyv)[NPF], bool& valid) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) k[i] = 0.f;
-        dyv = 0.f;
-        valid = false;
-        if (pi >= UT * B) return;
-        const int ui = pi % UT, b = pi / UT;
-        valid = t < lens_s[b];
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j < NPF; ++j) k[i][j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < NPF; ++j) dyv[j] = 0.f;
+        valid = b < B && t < lens_s[b < B ? b : 0];
         if (!valid) return;
         const bool pin = tp_in && (d == 0 || tp < lens_s[b]);
-        const size_t si = (((size_t)d * T + t) * B + b) * H + u0 + ui;
-        const size_t sp = (((size_t)d * T + (tp_in ? tp : 0)) * B + b) * H + u0 + ui;
-        const float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + ui;
-        dyv = p.dy[((size_t)t * B + b) * H + u0 + ui];
+        const size_t si = (((size_t)d * T + t) * B + b) * H + u0 + uq;
+        const size_t sp = (((size_t)d * T + (tp_in ? tp : 0)) * B + b) * H + u0 + uq;
+        const float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + uq;
+        ld4(p.dy + ((size_t)t * B + b) * H + u0 + uq, dyv);
         if (RNN == DS2_RNN_LSTM) {
-          const float gi = gp[0], gf = gp[H], gg = gp[2 * H], go = gp[3 * H];
-          const float c = p.aux[si], c_prev = pin ? p.aux[sp] : 0.f;
-          const float tc = fast_tanh(c);                  // the forward sweep produced h = o * fast_tanh(c)
-          k[0] = go * (1.f - tc * tc); k[1] = tc * go * (1.f - go); k[2] = gg * gi * (1.f - gi);
-          k[3] = c_prev * gf * (1.f - gf); k[4] = gi * (1.f - gg * gg); k[5] = gf;
+          float gi[NPF], gf[NPF], gg[NPF], go[NPF], c[NPF], c_prev[NPF] = {0.f, 0.f, 0.f, 0.f}, tc[NPF];
+          ld4(gp, gi); ld4(gp + H, gf); ld4(gp + 2 * H, gg); ld4(gp + 3 * H, go);
+          ld4(p.aux + si, c);
+          if (pin) ld4(p.aux + sp, c_prev);
+#pragma unroll
+          for (int j = 0; j < NPF; ++j) tc[j] = ex2_ftz(-2.f * LOG2E * c[j]);
+#pragma unroll
+          for (int j = 0; j < NPF; ++j) tc[j] = fmaf(2.f, rcp_ftz(1.f + tc[j]), -1.f);   // the forward used this tanh
+#pragma unroll
+          for (int j = 0; j < NPF; ++j) {
+            k[0][j] = go[j] * (1.f - tc[j] * tc[j]); k[1][j] = tc[j] * go[j] * (1.f - go[j]);
+            k[2][j] = gg[j] * gi[j] * (1.f - gi[j]); k[3][j] = c_prev[j] * gf[j] * (1.f - gf[j]);
+            k[4][j] = gi[j] * (1.f - gg[j] * gg[j]); k[5][j] = gf[j];
+          }
         } else if (RNN == DS2_RNN_GRU) {
-          const float r = gp[0], z = gp[H], n = gp[2 * H];
-          const float hn = p.aux[si], h_prev = pin ? p.hseq[sp] : 0.f;
-          const float cn = (1.f - z) * (1.f - n * n);
-          k[0] = cn * hn * r * (1.f - r); k[1] = (h_prev - n) * z * (1.f - z); k[2] = cn; k[3] = cn * r; k[4] = z;
+          float r[NPF], z[NPF], n[NPF], hn[NPF], h_prev[NPF] = {0.f, 0.f, 0.f, 0.f};
+          ld4(gp, r); ld4(gp + H, z); ld4(gp + 2 * H, n);
+          ld4(p.aux + si, hn);
+          if (pin) ld4(p.hseq + sp, h_prev);
+#pragma unroll
+          for (int j = 0; j < NPF; ++j) {
+            const float cn = (1.f - z[j]) * (1.f - n[j] * n[j]);
+            k[0][j] = cn * hn[j] * r[j] * (1.f - r[j]); k[1][j] = (h_prev[j] - n[j]) * z[j] * (1.f - z[j]);
+            k[2][j] = cn; k[3][j] = cn * r[j]; k[4][j] = z[j];
+          }
         } else {
-          const float hv = p.hseq[si];
-          k[0] = 1.f - hv * hv;
+          float hv[NPF];
+          ld4(p.hseq + si, hv);
+#pragma unroll
+          for (int j = 0; j < NPF; ++j) k[0][j] = 1.f - hv[j] * hv[j];
         }
       };
-      float kc[NPF][6], pdy[NPF];
-      bool pvalid[NPF];
-      if (single) {
-#pragma unroll
-        for (int j = 0; j < NPF; ++j) load_coefs(e + 128 * j, kc[j], pdy[j], pvalid[j]);
-      }
+      float kc[6][NPF], pdy[NPF];
+      bool pvalid = false;
+      if (single) load_coefs(b_own, kc, pdy, pvalid);
       if (step > 0) {
         if (e == 0) mbar_arrive_expect_tx(part_bar, part_tx);   // arm this step's phase (peers may already have sent)
         // send this CTA's partial tile: row (16q + ul), 32 columns split over the two half-warps
         mbar_wait(accum_bar, acc_phase);
         tc_fence_after();
         if (RES) {
-          // this step's MMAs ran, so the grid barrier was passed: every CTA's atomicMax of step-1 is final
-          s_prev = s_cur;
-          s_cur = pow2_scale_for(__uint_as_float(ld_acquire(gmax_d + step)), s_prev);
+          // this step's MMAs ran, so the grid barrier was passed: the maximum of step-1 the producer forwarded is final
+          sx_prev = sx_cur;
+          sx_cur = pow2_exp_for(*(volatile unsigned int*)(cta_max + 1), sx_prev);
+          s_cur = pow2f(sx_cur);
+          inv_prev = pow2f(-sx_prev);
         }
         if (e == 0) trace_stamp(p.trace, p.T, step, 5);
         for (int cb = 0; cb < NB; cb += 32) {
@@ -1211,87 +1270,96 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
         part_phase ^= 1;
       }
       if (e == 0) trace_stamp(p.trace, p.T, step, 7);
-      const float inv_prev = 1.f / s_prev;
-      // A batch of pairs: recurrent term from the four partial tiles (all remote loads issued first), gate
-      // backward from the coefficients.  The scaled fp16 copy (resident variant: the next step's MMA operand) is
-      // stored here; the fp32 gate gradients, which only the weight-gradient GEMMs after the sweep read, are
-      // returned in o[] (o[4]: GRU dGh_n) for store_dg().
-      auto finish4 = [&](int base, const float (&k)[NPF][6], const float (&dyv)[NPF], const bool (&valid)[NPF],
-                         float (&o)[NPF][5]) {
-        float r4[NPF][4];
+      // Four cells: recurrent term = sum of the four received slices, gate backward from the coefficients.  The
+      // scaled fp16 copy (resident variant: the next step's MMA operand) is stored here; the fp32 gate gradients,
+      // which only the weight-gradient GEMMs after the sweep read, are returned in o[] (o[4]: GRU dGh_n).
+      auto st_h4 = [&](__half* dst, const float (&v)[NPF]) {     // 4 scaled, saturated halves = one 8-byte store
+        const __half2 lo = __halves2half2(to_half_sat(v[0] * s_cur), to_half_sat(v[1] * s_cur));
+        const __half2 hi = __halves2half2(to_half_sat(v[2] * s_cur), to_half_sat(v[3] * s_cur));
+        uint2 pk;
+        pk.x = *reinterpret_cast<const unsigned int*>(&lo);
+        pk.y = *reinterpret_cast<const unsigned int*>(&hi);
+        *reinterpret_cast<uint2*>(dst) = pk;
+      };
+      auto finish4 = [&](int b, const float (&k)[6][NPF], const float (&dyv)[NPF], bool valid, float (&o)[5][NPF]) {
 #pragma unroll
-        for (int j = 0; j < NPF; ++j) {
-          const int pi = base + 128 * j;
-          const bool ld = step > 0 && valid[j];
-          const int off = ld ? (pi % UT) * PS + pi / UT : 0;
+        for (int i = 0; i < 5; ++i)
 #pragma unroll
-          for (int r = 0; r < 4; ++r) r4[j][r] = ld ? part[r * UT * PS + off] : 0.f;
+          for (int j = 0; j < NPF; ++j) o[i][j] = 0.f;
+        if (b >= B) return;
+        __half* hp16 = RES ? p.dg16 + (((size_t)t * B + b) * D + d) * GH + u0 + uq : nullptr;
+        if (!valid) {
+          if (RES) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) *reinterpret_cast<uint2*>(hp16 + g * H) = make_uint2(0u, 0u);
+          }
+          return;
         }
+        float dh[NPF];
 #pragma unroll
         for (int j = 0; j < NPF; ++j) {
-          const int pi = base + 128 * j;
-          o[j][0] = o[j][1] = o[j][2] = o[j][3] = o[j][4] = 0.f;
-          if (pi >= UT * B) continue;
-          const int ui = pi % UT, b = pi / UT, ci = ui * NBp + b;
-          __half* hp16 = RES ? p.dg16 + (((size_t)t * B + b) * D + d) * GH + u0 + ui : nullptr;
-          if (!valid[j]) {
-            if (RES) {
-#pragma unroll
-              for (int g = 0; g < G; ++g) hp16[g * H] = __float2half_rn(0.f);
-            }
-            continue;
+          float rec = 0.f;
+          if (step > 0) {
+            const float* pr = part + (uq + j) * PS + b;
+            rec = (pr[0] + pr[UT * PS]) + (pr[2 * UT * PS] + pr[3 * UT * PS]);
           }
-          const float rec = (r4[j][0] + r4[j][1]) + (r4[j][2] + r4[j][3]);
-          float dh = dyv[j] + (RES ? rec * inv_prev : rec);
-          if (RNN == DS2_RNN_LSTM) {
-            const float dc = fmaf(dh, k[j][0], cst[ci]);
-            o[j][0] = dc * k[j][2]; o[j][1] = dc * k[j][3]; o[j][2] = dc * k[j][4]; o[j][3] = dh * k[j][1];
-            cst[ci] = dc * k[j][5];
-            if (RES) {
-              lmax = fmaxf(lmax, fmaxf(fmaxf(fabsf(o[j][0]), fabsf(o[j][1])), fmaxf(fabsf(o[j][2]), fabsf(o[j][3]))));
+          dh[j] = dyv[j] + (RES ? rec * inv_prev : rec);
+        }
+        if (RNN == DS2_RNN_LSTM) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) hp16[g * H] = to_half_sat(o[j][g] * s_cur);
-            }
-          } else if (RNN == DS2_RNN_GRU) {
-            dh += cst[ci];
-            o[j][0] = dh * k[j][0]; o[j][1] = dh * k[j][1]; o[j][2] = dh * k[j][2]; o[j][4] = dh * k[j][3];
-            cst[ci] = dh * k[j][4];
-            if (RES) {
-              lmax = fmaxf(lmax, fmaxf(fabsf(o[j][0]), fmaxf(fabsf(o[j][1]), fabsf(o[j][4]))));
-              hp16[0] = to_half_sat(o[j][0] * s_cur); hp16[H] = to_half_sat(o[j][1] * s_cur);
-              hp16[2 * H] = to_half_sat(o[j][4] * s_cur);     // the h-side n-gate gradient (dGh_n)
-            }
-          } else {
-            o[j][0] = dh * k[j][0];
-            if (RES) { lmax = fmaxf(lmax, fabsf(o[j][0])); hp16[0] = to_half_sat(o[j][0] * s_cur); }
+          for (int j = 0; j < NPF; ++j) {
+            const int ci = (uq + j) * NBp + b;
+            const float dc = fmaf(dh[j], k[0][j], cst[ci]);
+            o[0][j] = dc * k[2][j]; o[1][j] = dc * k[3][j]; o[2][j] = dc * k[4][j]; o[3][j] = dh[j] * k[1][j];
+            cst[ci] = dc * k[5][j];
+            lmax = fmaxf(lmax, fmaxf(fmaxf(fabsf(o[0][j]), fabsf(o[1][j])), fmaxf(fabsf(o[2][j]), fabsf(o[3][j]))));
           }
+          if (RES) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) st_h4(hp16 + g * H, o[g]);
+          }
+        } else if (RNN == DS2_RNN_GRU) {
+#pragma unroll
+          for (int j = 0; j < NPF; ++j) {
+            const int ci = (uq + j) * NBp + b;
+            const float dht = dh[j] + cst[ci];
+            o[0][j] = dht * k[0][j]; o[1][j] = dht * k[1][j]; o[2][j] = dht * k[2][j]; o[4][j] = dht * k[3][j];
+            cst[ci] = dht * k[4][j];
+            lmax = fmaxf(lmax, fmaxf(fabsf(o[0][j]), fmaxf(fabsf(o[1][j]), fabsf(o[4][j]))));
+          }
+          if (RES) {
+            st_h4(hp16, o[0]); st_h4(hp16 + H, o[1]);
+            st_h4(hp16 + 2 * H, o[4]);                        // the h-side n-gate gradient (dGh_n)
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NPF; ++j) {
+            o[0][j] = dh[j] * k[0][j];
+            lmax = fmaxf(lmax, fabsf(o[0][j]));
+          }
+          if (RES) st_h4(hp16, o[0]);
         }
       };
-      auto store_dg = [&](int pi, const float (&o)[5]) {
-        const int ui = pi % UT, b = pi / UT;
-        float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + ui;
+      auto st4 = [](float* dst, const float (&v)[NPF]) {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      };
+      auto store_dg = [&](int b, const float (&o)[5][NPF]) {
+        float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + uq;
 #pragma unroll
-        for (int g = 0; g < G; ++g) gp[g * H] = o[g];
-        if (RNN == DS2_RNN_GRU) p.aux[(((size_t)d * T + t) * B + b) * H + u0 + ui] = o[4];
+        for (int g = 0; g < G; ++g) st4(gp + g * H, o[g]);
+        if (RNN == DS2_RNN_GRU) st4(p.aux + (((size_t)d * T + t) * B + b) * H + u0 + uq, o[4]);
       };
       // the non-resident variants stream the fp32 gate gradients themselves: nothing can be deferred there
       const bool defer = RES && p.defer && single;
-      float sv[NPF][5];
+      float sv[5][NPF];
       if (single) {
-        finish4(e, kc, pdy, pvalid, sv);
-        if (!defer) {
-#pragma unroll
-          for (int j = 0; j < NPF; ++j)
-            if (e + 128 * j < UT * B) store_dg(e + 128 * j, sv[j]);
-        }
+        finish4(b_own, kc, pdy, pvalid, sv);
+        if (!defer && b_own < B) store_dg(b_own, sv);
       } else {
-        for (int base = e; base < UT * B; base += 128 * NPF) {
-#pragma unroll
-          for (int j = 0; j < NPF; ++j) load_coefs(base + 128 * j, kc[j], pdy[j], pvalid[j]);
-          finish4(base, kc, pdy, pvalid, sv);
-#pragma unroll
-          for (int j = 0; j < NPF; ++j)
-            if (base + 128 * j < UT * B) store_dg(base + 128 * j, sv[j]);
+        for (int b = b_own; b < B; b += 32) {
+          load_coefs(b, kc, pdy, pvalid);
+          finish4(b, kc, pdy, pvalid, sv);
+          store_dg(b, sv);
         }
       }
       if (RES) {
@@ -1314,11 +1382,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
         trace_stamp_ns(p.trace, p.T, step, 12);
       }
       if (defer) {
-#pragma unroll
-        for (int j = 0; j < NPF; ++j) {
-          const int pi = e + 128 * j;
-          if (pi < UT * B) store_dg(pi, sv[j]);
-        }
+        if (b_own < B) store_dg(b_own, sv);
         if (e == 0) trace_stamp(p.trace, p.T, step, 13);
       }
     }
@@ -1366,7 +1430,8 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
   using namespace rp;
   const int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
   const int GH = G * a.H;
-  if (a.H % 64 != 0 || GH % 4 != 0 || (GH / 4) % 64 != 0 || (GH / 4) / 64 > 128) return 1;
+  if (a.H % 64 != 0 || GH % 4 != 0 || (GH / 4) % 64 != 0 || (GH / 4) / 64 > 120) return 1;   // <= 32 group barriers
+  if (!vec_ok(a.gates, a.hseq, a.aux, a.dy)) return 1;
   if (ws_bytes < splitk_res_ws_bytes(G, a.T, a.B, a.H, a.D)) return 1;
   PersistParams p{};
   p.T = a.T; p.B = a.B; p.NB = (a.B + 7) / 8 * 8; p.H = a.H; p.D = a.D; p.NT = a.H / 64; p.G = G;
@@ -1422,6 +1487,11 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
     if (rc) return rc;
     rc = make_tmap_f16(&p.tmV[d], p.dg16, 2, a.D * GH, a.T * a.B, 1, (size_t)a.D * GH, 0, 64, a.B, 1);
     if (rc) return rc;
+    p.box3 = ((GH / 4) / 64) % 4 == 0;
+    if (p.box3) {
+      rc = make_tmap_f16(&p.tmV3[d], p.dg16, 3, 64, a.T * a.B, a.D * GH / 64, (size_t)a.D * GH, 64, 64, p.NB, 4);
+      if (rc) return rc;
+    }
     // step-0 scale: |dGh| <= |dh| = |dY[t_first]| for every cell type
     const int t_first = d == 0 ? a.T - 1 : 0;
     DS2_LAUNCH(absmax_kernel, 64, 256, 0, st, (size_t)a.B * a.H, a.dy + (size_t)t_first * a.B * a.H,
@@ -1451,6 +1521,7 @@ static int launch_bwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
     if (rc != 1) return rc;
   }
   if (a.H % 64 != 0 || (GH / 4) % BK != 0 || GH % 4 != 0) return 1;
+  if (!vec_ok(a.gates, a.hseq, a.aux, a.dy)) return 1;
   PersistParams p{};
   p.T = a.T; p.B = a.B; p.NB = (a.B + 7) / 8 * 8; p.H = a.H; p.D = a.D; p.NT = a.H / 64; p.G = G;
   p.training = 1;
