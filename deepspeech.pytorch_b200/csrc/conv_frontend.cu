@@ -368,46 +368,63 @@ __global__ void __launch_bounds__(256) conv2_dw_kernel(int B, int T, const float
 }
 
 // conv1: dw1[co][kh][kw] = sum_{b,d,t} dz1[b,co,d,t] * x[b,2d+kh-20,2t+kw-5]
-// CTA = (group of 8 kh, b); thread = (kh_local, co) x 11 kw accumulators.
-__global__ void __launch_bounds__(256) conv1_dw_kernel(int B, int Tin, int T, const float* __restrict__ dz1,
+// CTA = (group of 14 kh, b, half of the d range); thread = (kh_local, group of 4 co) with 4 x 11 kw accumulators:
+// per 4 time steps 17 window loads + 4 vector loads feed 176 FFMAs (the earlier 1 co x 11 kw blocking was
+// shared-memory bound at 21 loads per 44 FFMAs).
+constexpr int C1_KG = 14, C1_TW = 64, C1_XW = 2 * C1_TW + 12, C1_DSPLIT = 2;
+__global__ void __launch_bounds__(128) conv1_dw_kernel(int B, int Tin, int T, const float* __restrict__ dz1,
                                                        const float* __restrict__ x, float* __restrict__ dw1) {
-  constexpr int D1 = DS2_CONV1_D, F = DS2_NUM_FREQ, TW = 64, XW = 2 * TW + 12;  // 140 columns
-  __shared__ float dsm[TW][33];    // [t][co]
-  __shared__ float xsm[8][XW];     // [kh_local][2t+kw]
-  const int kh0 = blockIdx.x * 8, b = blockIdx.y, tid = threadIdx.x;
-  const int khl = tid / 32, co = tid % 32, kh = kh0 + khl;
-  float acc[11];
+  constexpr int D1 = DS2_CONV1_D, F = DS2_NUM_FREQ, TW = C1_TW, XW = C1_XW;
+  __shared__ __align__(16) float dsm[TW][CO];     // [t][co]
+  __shared__ float xsm[C1_KG][XW];                // [kh_local][2t+kw]
+  const int kh0 = blockIdx.x * C1_KG, b = blockIdx.y, tid = threadIdx.x;
+  const int dper = (D1 + C1_DSPLIT - 1) / C1_DSPLIT, d0 = blockIdx.z * dper, d1 = min(D1, d0 + dper);
+  const int cog = tid % 8, khl = tid / 8, kh = kh0 + khl;      // khl 14, 15: loaders only
+  const bool worker = khl < C1_KG && kh < 41;
+  const int khr = worker ? khl : 0;
+  float acc[4][11];
 #pragma unroll
-  for (int k = 0; k < 11; ++k) acc[k] = 0.f;
-  for (int d = 0; d < D1; ++d) {
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int k = 0; k < 11; ++k) acc[c][k] = 0.f;
+  for (int d = d0; d < d1; ++d) {
     for (int t0 = 0; t0 < T; t0 += TW) {
-      for (int idx = tid; idx < CO * TW; idx += 256) {
-        int tt = idx % TW, c2 = idx / TW, t = t0 + tt;
+      for (int idx = tid; idx < CO * TW; idx += 128) {
+        const int tt = idx % TW, c2 = idx / TW, t = t0 + tt;
         dsm[tt][c2] = (t < T) ? dz1[(((size_t)b * CO + c2) * D1 + d) * T + t] : 0.f;
       }
-      for (int idx = tid; idx < 8 * XW; idx += 256) {
-        int cc = idx % XW, kl = idx / XW, r = 2 * d + kh0 + kl - 20, c = 2 * t0 + cc - 5;
+      for (int idx = tid; idx < C1_KG * XW; idx += 128) {
+        const int cc = idx % XW, kl = idx / XW, r = 2 * d + kh0 + kl - 20, c = 2 * t0 + cc - 5;
         xsm[kl][cc] = (kh0 + kl < 41 && r >= 0 && r < F && c >= 0 && c < Tin) ? x[((size_t)b * F + r) * Tin + c] : 0.f;
       }
       __syncthreads();
+      if (worker) {
 #pragma unroll 1
-      for (int tb = 0; tb < TW; tb += 4) {
-        float win[17];
+        for (int tb = 0; tb < TW; tb += 4) {
+          float win[17];
 #pragma unroll
-        for (int i = 0; i < 17; ++i) win[i] = xsm[khl][2 * tb + i];
+          for (int i = 0; i < 17; ++i) win[i] = xsm[khr][2 * tb + i];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float dv = dsm[tb + j][co];
+          for (int j = 0; j < 4; ++j) {
+            const float4 dv = *reinterpret_cast<const float4*>(&dsm[tb + j][cog * 4]);
 #pragma unroll
-          for (int k = 0; k < 11; ++k) acc[k] = fmaf(dv, win[2 * j + k], acc[k]);
+            for (int k = 0; k < 11; ++k) {
+              const float a = win[2 * j + k];
+              acc[0][k] = fmaf(dv.x, a, acc[0][k]); acc[1][k] = fmaf(dv.y, a, acc[1][k]);
+              acc[2][k] = fmaf(dv.z, a, acc[2][k]); acc[3][k] = fmaf(dv.w, a, acc[3][k]);
+            }
+          }
         }
       }
       __syncthreads();
     }
   }
-  if (kh < 41)
+  if (worker) {
 #pragma unroll
-    for (int k = 0; k < 11; ++k) atomicAdd(&dw1[((size_t)co * 41 + kh) * 11 + k], acc[k]);
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int k = 0; k < 11; ++k) atomicAdd(&dw1[((size_t)(cog * 4 + c) * 41 + kh) * 11 + k], acc[c][k]);
+  }
 }
 
 // ---- host helpers -------------------------------------------------------------------------------
@@ -436,7 +453,7 @@ int conv2_wgrad_tc(const float* dz2, const float* a1, float* a1_shifted, int B, 
 struct ConvWs {
   float *wpk1, *wpk2, *wTe, *wTo, *du2, *da1;
   float *taps_f, *taps_b, *cl;     // tensor-core path: packed taps (21x352x32 each), channels-last staging
-  float* shifted;                  // tensor-core weight gradient: a1 shifted by 1,2,3 time steps
+  float* shifted;                  // tensor-core weight gradient: a1 delayed by 0,1,2,3 time steps
   double* sums;   // 4 x 64 doubles: fwd stats 1, fwd stats 2, bwd sums 2, bwd sums 1
 };
 static size_t conv_ws_carve(int B, int T, void* base, ConvWs* w) {
@@ -454,7 +471,7 @@ static size_t conv_ws_carve(int B, int T, void* base, ConvWs* w) {
   p = (float*)take((size_t)21 * 352 * 32 * 4); if (w) w->taps_f = p;
   p = (float*)take((size_t)21 * 352 * 32 * 4); if (w) w->taps_b = p;
   p = (float*)take((size_t)B * CO * DS2_CONV1_D * Tp * 4); if (w) w->cl = p;
-  p = (float*)take((size_t)3 * B * CO * DS2_CONV1_D * (Tp + 4) * 4); if (w) w->shifted = p;
+  p = (float*)take((size_t)4 * B * CO * DS2_CONV1_D * (Tp + 4) * 4); if (w) w->shifted = p;
   return off;
 }
 
@@ -576,7 +593,7 @@ int ds2_conv_frontend_bwd(int B, int T, const float* x, const int32_t* out_len, 
   DS2_LAUNCH(bn_bwd_params2d_kernel, 1, 32, 0, st, s1, dg1, dbe1);
   DS2_LAUNCH(bn_bwd_apply_kernel, dim3(cdiv(D1 * Tp, 256), CO, B), 256, 0, st, B, D1, Tp, 1.0 / ((double)B * D1 * Tp),
              z1, stats, g1, out_len, s1, W.da1, db1);
-  DS2_LAUNCH(conv1_dw_kernel, dim3(6, B), 256, 0, st, B, T, Tp, W.da1, x, dw1);
+  DS2_LAUNCH(conv1_dw_kernel, dim3(3, B, C1_DSPLIT), 128, 0, st, B, T, Tp, W.da1, x, dw1);
   return DS2_OK;
 }
 

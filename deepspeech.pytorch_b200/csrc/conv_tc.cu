@@ -261,8 +261,9 @@ int conv_tc_run(const float* in_cl, int B, int T, int R_in, int R_out, const flo
 // ---- weight gradient of conv2 on tensor cores ---------------------------------------------------------
 //   dW[co][ci][kh][kw] = sum_{b,d,t} dz2[b,co,d,t] * a1[b,ci,2d+kh-10,t+kw-5]
 // GEMM over time (K = t): A = dz2[b,:,d,t-chunk] (32 co rows, M padded to 64), B rows (kw,ci) =
-// a1[b,ci,r,t-chunk shifted by kw-5] (eleven 4 KB TMA boxes, N = 352), both operands K-major straight
-// out of the NCHW tensors.  A CTA owns one kh and a slice of the (b,d) pairs, accumulates all of them
+// a1[b,ci,r,t-chunk shifted by kw-5] (N = 352), both operands K-major.  The producer thread needs ~110 cycles
+// per TMA instruction, so the eleven shifted 4 KB tiles are fetched with four boxes that span the "shift copy"
+// dimension of a 4-copy tensor (see shift_copies_kernel); the N blocks then sit in the order KW_OF_BLOCK.  A CTA owns one kh and a slice of the (b,d) pairs, accumulates all of them
 // in TMEM and finally adds its 32 x 352 tile into dW with fp32 atomics.
 namespace wg {
 constexpr int KT = 32;                               // time steps per K chunk (128 bytes)
@@ -276,11 +277,15 @@ constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256;
 
 struct WgradParams {
   CUtensorMap tmDz;   // 4-D (T, 41, 32 co, B)
-  CUtensorMap tmA1;   // 4-D (T, 81, 32 ci, B)
-  CUtensorMap tmA1s;  // 5-D (T, 81, 32 ci, B, 3): copies of a1 shifted left by 1, 2, 3 time steps
+  CUtensorMap tmS4;   // 5-D (T+4, 81, 32 ci, B, 4 copies): a1 delayed by 0, 1, 2, 3 time steps; box = 4 copies
+  CUtensorMap tmS2;   // same tensor, box = 2 copies
+  CUtensorMap tmS1;   // same tensor, box = 1 copy
   int B, T, slices;
   float* dw2;
 };
+// shared-memory N block j (32 ci rows each) holds tap kw = KW_OF_BLOCK[j]:
+//   box (t0-4, copies 0,1) -> kw 1,0 | (t0, copies 0..3) -> kw 5,4,3,2 | (t0+4, copies 0..3) -> kw 9,8,7,6 | (t0+8, copy 3) -> kw 10
+__constant__ int KW_OF_BLOCK[11] = {1, 0, 5, 4, 3, 2, 9, 8, 7, 6, 10};
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
@@ -301,8 +306,8 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
 }
 
 // TMA needs 16-byte aligned box starts in the innermost dimension, so a shift by sh = kw-5 time steps is
-// split into a multiple of 4 (the box coordinate) and s = 0..3 (which pre-shifted copy is read):
-//   a1r[s-1][row][t'] = a1[row][t'-s]  for t' in [0, T+4)  (0 outside the row; rows padded to T+4 so that the
+// split into a multiple of 4 (the box coordinate) and s = 0..3 (which delayed copy is read):
+//   a1r[s][row][t'] = a1[row][t'-s]  for t' in [0, T+4)  (0 outside the row; rows padded to T+4 so that the
 //   shifted tail stays in bounds),  a1[t + sh] = a1r[s][t + sh + s]  with (sh + s) % 4 == 0.
 __global__ void shift_copies_kernel(size_t rows, int T, const float* __restrict__ a1, float* __restrict__ a1r) {
   const int Tp = T + 4;
@@ -311,9 +316,9 @@ __global__ void shift_copies_kernel(size_t rows, int T, const float* __restrict_
     const int t = (int)(i % Tp);
     const float* src = a1 + (i / Tp) * T;
 #pragma unroll
-    for (int sft = 1; sft <= 3; ++sft) {
+    for (int sft = 0; sft <= 3; ++sft) {
       const int ts = t - sft;
-      a1r[(size_t)(sft - 1) * n + i] = (ts >= 0 && ts < T) ? src[ts] : 0.f;
+      a1r[(size_t)sft * n + i] = (ts >= 0 && ts < T) ? src[ts] : 0.f;
     }
   }
 }
@@ -336,7 +341,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) conv2_wgrad_tc_kernel(const __
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmDz);
-    tma_prefetch_desc(&p.tmA1);
+    tma_prefetch_desc(&p.tmS4);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(accum_bar, 1);
     fence_barrier_init();
@@ -366,12 +371,11 @@ __global__ void __launch_bounds__(wg::THREADS, 1) conv2_wgrad_tc_kernel(const __
           mbar_arrive_expect_tx(&full[s], (uint32_t)(32 * 128 + cv::NN * 128));
           uint8_t* st = smem + s * STAGE_BYTES;
           tma_load_4d(st, &p.tmDz, &full[s], kt * KT, d, 0, b);
-#pragma unroll 1
-          for (int kw = 0; kw < cv::KW; ++kw) {
-            const int sh = kw - 5, sft = (4 - (((sh % 4) + 4) % 4)) % 4;      // (sh + sft) % 4 == 0
-            if (sft == 0) tma_load_4d(st + A_BYTES + kw * 32 * 128, &p.tmA1, &full[s], kt * KT + sh, r, 0, b);
-            else tma_load_5d(st + A_BYTES + kw * 32 * 128, &p.tmA1s, &full[s], kt * KT + sh + sft, r, 0, b, sft - 1);
-          }
+          uint8_t* nb = st + A_BYTES;                      // N blocks of 32 rows x 128 B
+          tma_load_5d(nb, &p.tmS2, &full[s], kt * KT - 4, r, 0, b, 0);
+          tma_load_5d(nb + 2 * 4096, &p.tmS4, &full[s], kt * KT, r, 0, b, 0);
+          tma_load_5d(nb + 6 * 4096, &p.tmS4, &full[s], kt * KT + 4, r, 0, b, 0);
+          tma_load_5d(nb + 10 * 4096, &p.tmS1, &full[s], kt * KT + 8, r, 0, b, 3);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -404,9 +408,10 @@ __global__ void __launch_bounds__(wg::THREADS, 1) conv2_wgrad_tc_kernel(const __
     tc_fence_after();
     if (q < 2) {
       const int co = q * 16 + lane;
-      for (int kw = 0; kw < cv::KW; ++kw) {
+      for (int blk = 0; blk < cv::KW; ++blk) {
+        const int kw = KW_OF_BLOCK[blk];
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kw * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * 32), v);
         if (lane < 16) {
 #pragma unroll
           for (int ci = 0; ci < 32; ++ci)
@@ -422,7 +427,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) conv2_wgrad_tc_kernel(const __
 
 // dz2: (B,32,41,T) NCHW gate... conv2 output gradient; a1: (B,32,81,T) NCHW; dw2 (32,32,21,11) must be zeroed.
 // Returns 1 when the shape is not eligible (row pitch T*4 bytes must be a multiple of 16).
-int conv2_wgrad_tc(const float* dz2, const float* a1, float* a1_shifted /* 3*B*32*81*(T+4) floats */, int B, int T,
+int conv2_wgrad_tc(const float* dz2, const float* a1, float* a1_shifted /* 4*B*32*81*(T+4) floats */, int B, int T,
                    float* dw2, cudaStream_t st) {
   if (T % 4 != 0) return 1;
   WgradParams p{};
@@ -430,10 +435,16 @@ int conv2_wgrad_tc(const float* dz2, const float* a1, float* a1_shifted /* 3*B*3
     const size_t rows = (size_t)B * 32 * 81;
     DS2_LAUNCH(shift_copies_kernel, 148 * 8, 256, 0, st, rows, T, a1, a1_shifted);
     const unsigned long long Tq = (unsigned long long)T + 4;
-    unsigned long long dims[5] = {Tq, 81ull, 32ull, (unsigned long long)B, 3ull};
+    unsigned long long dims[5] = {Tq, 81ull, 32ull, (unsigned long long)B, 4ull};
     unsigned long long str[4] = {Tq * 4, 81ull * Tq * 4, 32ull * 81 * Tq * 4, (unsigned long long)rows * Tq * 4};
-    unsigned int box[5] = {32u, 1u, 32u, 1u, 1u};
-    int rc = make_tmap_nd_f32(&p.tmA1s, a1_shifted, 5, dims, str, box);
+    unsigned int box[5] = {32u, 1u, 32u, 1u, 4u};
+    int rc = make_tmap_nd_f32(&p.tmS4, a1_shifted, 5, dims, str, box);
+    if (rc) return rc;
+    box[4] = 2u;
+    rc = make_tmap_nd_f32(&p.tmS2, a1_shifted, 5, dims, str, box);
+    if (rc) return rc;
+    box[4] = 1u;
+    rc = make_tmap_nd_f32(&p.tmS1, a1_shifted, 5, dims, str, box);
     if (rc) return rc;
   }
   {
@@ -441,13 +452,6 @@ int conv2_wgrad_tc(const float* dz2, const float* a1, float* a1_shifted /* 3*B*3
     unsigned long long str[3] = {(unsigned long long)T * 4, (unsigned long long)41 * T * 4, (unsigned long long)32 * 41 * T * 4};
     unsigned int box[4] = {32u, 1u, 32u, 1u};
     int rc = make_tmap_4d_f32(&p.tmDz, dz2, dims, str, box);
-    if (rc) return rc;
-  }
-  {
-    unsigned long long dims[4] = {(unsigned long long)T, 81ull, 32ull, (unsigned long long)B};
-    unsigned long long str[3] = {(unsigned long long)T * 4, (unsigned long long)81 * T * 4, (unsigned long long)32 * 81 * T * 4};
-    unsigned int box[4] = {32u, 1u, 32u, 1u};
-    int rc = make_tmap_4d_f32(&p.tmA1, a1, dims, str, box);
     if (rc) return rc;
   }
   p.B = B; p.T = T; p.slices = 7; p.dw2 = dw2;
