@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(256) conv2_dw_kernel(int B, int T, const float
 // CTA = (group of 14 kh, b, half of the d range); thread = (kh_local, group of 4 co) with 4 x 11 kw accumulators:
 // per 4 time steps 17 window loads + 4 vector loads feed 176 FFMAs (the earlier 1 co x 11 kw blocking was
 // shared-memory bound at 21 loads per 44 FFMAs).
-constexpr int C1_KG = 14, C1_TW = 64, C1_XW = 2 * C1_TW + 12, C1_DSPLIT = 2;
+constexpr int C1_KG = 14, C1_TW = 64, C1_XW = 2 * C1_TW + 12, C1_DSPLIT = 6;
 __global__ void __launch_bounds__(128) conv1_dw_kernel(int B, int Tin, int T, const float* __restrict__ dz1,
                                                        const float* __restrict__ x, float* __restrict__ dw1) {
   constexpr int D1 = DS2_CONV1_D, F = DS2_NUM_FREQ, TW = C1_TW, XW = C1_XW;

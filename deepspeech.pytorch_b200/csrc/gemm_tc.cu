@@ -66,8 +66,14 @@ static int make_tmap_2d_sw(CUtensorMap* out, const float* base, int rows, int co
   return DS2_OK;
 }
 
+static int make_tmap_3d_sw(CUtensorMap* out, const float* base, int d0, int d1, int d2, size_t stride1, size_t stride2,
+                           int box0, int box1, int box2, CUtensorMapSwizzle sw);
 int make_tmap_3d(CUtensorMap* out, const float* base, int d0, int d1, int d2, size_t stride1, size_t stride2,
                  int box0, int box1, int box2) {
+  return make_tmap_3d_sw(out, base, d0, d1, d2, stride1, stride2, box0, box1, box2, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+static int make_tmap_3d_sw(CUtensorMap* out, const float* base, int d0, int d1, int d2, size_t stride1, size_t stride2,
+                           int box0, int box1, int box2, CUtensorMapSwizzle sw) {
   int rc = load_encode();
   if (rc) return rc;
   cuuint64_t gdim[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
@@ -75,7 +81,7 @@ int make_tmap_3d(CUtensorMap* out, const float* base, int d0, int d1, int d2, si
   cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, (cuuint32_t)box2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_encode(out, g_tmap_dtype, 3, const_cast<float*>(base), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(3d %d,%d,%d box %d,%d,%d) failed: %d", d0, d1, d2, box0, box1, box2, (int)r);
@@ -141,21 +147,35 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, int d0, int d1, 
 }
 
 // ---- kernel ---------------------------------------------------------------------------------------
+// NMB = number of 128-row M blocks per CTA.  With one block (tile 128 x 256) a K chunk moves 48 KB from L2 for
+// 512 tensor-pipe cycles = 94 B/cycle/SM, more than twice the ~42 B/cycle/SM the L2 can deliver to all SMs at
+// once: the kernel is L2-bandwidth bound at ~50 % of the TF32 peak (ncu: tensor pipe 54 % active).  With two
+// blocks (tile 256 x 256, two accumulators in the 512 TMEM columns, B tile shared) it is 64 KB per 1024 cycles.
 namespace gtc {
-constexpr int BM = 128, BN = 256, BK = 32, STAGES = 4;
-constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int THREADS = 192;
+constexpr int BN = 256, BK = 32, THREADS = 192;
+// STG = pipeline stages.  (NMB 1, STG 2) fits two CTAs per SM (2 x 97 KB shared memory, 2 x 256 TMEM columns):
+// one CTA's epilogue then overlaps the other's main loop, which matters for short K (32 chunks at K = 1024).
+template <int NMB, int STG>
+struct Cfg {
+  static constexpr int BM = 128 * NMB;
+  static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = STG;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 256 * NMB;
+  static constexpr int CTAS_PER_SM = (NMB == 1 && STG == 2) ? 2 : 1;
+};
 }  // namespace gtc
 
 // MN-major operand tile (the matrix is stored (K, MN) row-major, i.e. "transposed" for this GEMM).  32-bit
 // MN-major operands have exactly one legal shared-memory layout on tcgen05, SWIZZLE_128B_BASE32B (descriptor
 // layout type 1; with the plain 128B swizzle the MMA returns zeros): rows of 32 mn elements (128 B), the
 // 32-byte chunk index of a row XOR-ed with (k & 3), repeating every 4 k-rows (512 B) — what the TMA unit
-// produces with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  The tile is loaded as ROWS/32 boxes of (32 mn x 32 k):
-// box i occupies 4 KB; leading byte offset = distance between consecutive 32-wide MN blocks (4096), stride byte
-// offset = distance between 4-row k groups (512); one MMA (K = 8) consumes two groups, so the k-step advance
-// is 1024 B.  No transpose pass is needed.
+// produces with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  The tile is ROWS/32 blocks of (32 mn x 32 k), 4 KB each;
+// leading byte offset = distance between consecutive 32-wide MN blocks (4096), stride byte offset = distance
+// between 4-row k groups (512); one MMA (K = 8) consumes two groups, so the k-step advance is 1024 B.  All blocks
+// of a tile come from ONE 3-D box (mn in block, k, block) when the MN extent is a multiple of 32 (the single
+// producer thread needs ~110 cycles per TMA instruction: 12 boxes per stage made it the bottleneck); otherwise
+// one 2-D box per block.  No transpose pass is needed.
 __device__ __forceinline__ uint64_t smem_desc_mn(uint32_t smem_addr, uint32_t layout, uint32_t lbo_bytes,
                                                  uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -167,21 +187,27 @@ __device__ __forceinline__ uint64_t smem_desc_mn(uint32_t smem_addr, uint32_t la
   return d;
 }
 
-template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(gtc::THREADS, 1)
+// gridDim.z > 1: split-K, every CTA adds its partial tile into C with vector atomics (C holds beta * C_old,
+// prepared by the host).
+template <bool A_MN, bool B_MN, int NMB, int STG>
+__global__ void __launch_bounds__(gtc::THREADS, gtc::Cfg<NMB, STG>::CTAS_PER_SM)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-               float alpha, float beta, float* __restrict__ C, int ldc, unsigned int mn_cfg) {
+               float alpha, float beta, float* __restrict__ C, int ldc, unsigned int mn_cfg, int mn3d) {
   using namespace gtc;
   using namespace tc;
+  using G = Cfg<NMB, STG>;
+  constexpr int BM = G::BM, STAGES = G::STAGES, STAGE_BYTES = G::STAGE_BYTES, A_BYTES = G::A_BYTES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* accum_bar = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int nk = (K + BK - 1) / BK;
+  const int nk_all = (K + BK - 1) / BK, per = (nk_all + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int kb0 = (int)blockIdx.z * per, kb1 = min(nk_all, kb0 + per), nk = max(0, kb1 - kb0);
+  const bool split = gridDim.z > 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -190,7 +216,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<G::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -198,34 +224,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int it = 0; it < nk; ++it) {
+        const int kb = kb0 + it, s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+        uint8_t* sa = smem + s * STAGE_BYTES;
         if (A_MN) {
+          if (mn3d & 1) {
+            tma_load_3d(sa, &tmA, &full[s], 0, kb * BK, m0 / 32);
+          } else {
 #pragma unroll
-          for (int i = 0; i < BM / 32; ++i)
-            tma_load_2d(smem + s * STAGE_BYTES + i * 4096, &tmA, &full[s], m0 + i * 32, kb * BK);
+            for (int i = 0; i < BM / 32; ++i) tma_load_2d(sa + i * 4096, &tmA, &full[s], m0 + i * 32, kb * BK);
+          }
         } else {
-          tma_load_2d(smem + s * STAGE_BYTES, &tmA, &full[s], kb * BK, m0);
+          tma_load_2d(sa, &tmA, &full[s], kb * BK, m0);
         }
         if (B_MN) {
+          if (mn3d & 2) {
+            tma_load_3d(sa + A_BYTES, &tmB, &full[s], 0, kb * BK, n0 / 32);
+          } else {
 #pragma unroll
-          for (int i = 0; i < BN / 32; ++i)
-            tma_load_2d(smem + s * STAGE_BYTES + A_BYTES + i * 4096, &tmB, &full[s], n0 + i * 32, kb * BK);
+            for (int i = 0; i < BN / 32; ++i) tma_load_2d(sa + A_BYTES + i * 4096, &tmB, &full[s], n0 + i * 32, kb * BK);
+          }
         } else {
-          tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &tmB, &full[s], kb * BK, n0);
+          tma_load_2d(sa + A_BYTES, &tmB, &full[s], kb * BK, n0);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = instr_desc(FMT_TF32, BM, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+      constexpr uint32_t idesc = instr_desc(FMT_TF32, 128, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
       const uint32_t mn_layout = mn_cfg & 7u, lbo = ((mn_cfg >> 4) & 0x3FFFu) << 4, sbo = (mn_cfg >> 18) << 4;
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES), b_addr = smem_u32(smem + s * STAGE_BYTES + A_BYTES);
@@ -234,52 +267,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // k-step: K-major +32 B inside the 128B swizzle row; MN-major +1024 B (the next group of 8 k-rows)
         constexpr uint64_t a_adv = A_MN ? 64 : 2, b_adv = B_MN ? 64 : 2;
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k)
-          mma_tf32(tmem_base, adesc + (uint64_t)k * a_adv, bdesc + (uint64_t)k * b_adv, idesc, (kb | k) != 0);
+        for (int mb = 0; mb < NMB; ++mb) {
+          // M block mb: rows 128*mb.. of the A tile are 16 KB further in either layout; its accumulator 256 columns
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k)
+            mma_tf32(tmem_base + (uint32_t)(mb * 256), adesc + (uint64_t)(mb * 1024) + (uint64_t)k * a_adv,
+                     bdesc + (uint64_t)k * b_adv, idesc, (it | k) != 0);
+        }
         mma_commit(&empty[s]);             // stage reusable when these MMAs have read it
       }
       mma_commit(accum_bar);               // accumulator complete
     }
-  } else {
+  } else if (nk > 0) {
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const int q = warp % 4;                // TMEM lane quarter this warp may read
-    const int row = m0 + q * 32 + lane;
     const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      const int col0 = n0 + c * 32;
-      if (col0 >= N) break;                // warp-uniform
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      if (row < M) {
-        float* cp = C + (size_t)row * ldc + col0;
-        if (vec_ok && col0 + 32 <= N) {
+    for (int mb = 0; mb < NMB; ++mb) {
+      const int row = m0 + mb * 128 + q * 32 + lane;
+      if (m0 + mb * 128 >= M) break;       // warp-uniform
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= N) break;              // warp-uniform
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * 256 + c * 32), v);
+        if (row < M) {
+          float* cp = C + (size_t)row * ldc + col0;
+          if (vec_ok && col0 + 32 <= N) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o = make_float4(alpha * v[4 * j], alpha * v[4 * j + 1], alpha * v[4 * j + 2], alpha * v[4 * j + 3]);
-            if (beta != 0.f) {
-              float4 old = *reinterpret_cast<const float4*>(cp + 4 * j);
-              o.x = fmaf(beta, old.x, o.x); o.y = fmaf(beta, old.y, o.y);
-              o.z = fmaf(beta, old.z, o.z); o.w = fmaf(beta, old.w, o.w);
+            for (int j = 0; j < 8; ++j) {
+              float4 o = make_float4(alpha * v[4 * j], alpha * v[4 * j + 1], alpha * v[4 * j + 2], alpha * v[4 * j + 3]);
+              if (split) {
+                atomicAdd(reinterpret_cast<float4*>(cp + 4 * j), o);
+              } else {
+                if (beta != 0.f) {
+                  float4 old = *reinterpret_cast<const float4*>(cp + 4 * j);
+                  o.x = fmaf(beta, old.x, o.x); o.y = fmaf(beta, old.y, o.y);
+                  o.z = fmaf(beta, old.z, o.z); o.w = fmaf(beta, old.w, o.w);
+                }
+                *reinterpret_cast<float4*>(cp + 4 * j) = o;
+              }
             }
-            *reinterpret_cast<float4*>(cp + 4 * j) = o;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) {
+                float o = alpha * v[j];
+                if (split) {
+                  atomicAdd(cp + j, o);
+                } else {
+                  if (beta != 0.f) o = fmaf(beta, cp[j], o);
+                  cp[j] = o;
+                }
+              }
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < N) {
-              float o = alpha * v[j];
-              if (beta != 0.f) o = fmaf(beta, cp[j], o);
-              cp[j] = o;
-            }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+  if (warp == 1) tmem_dealloc<G::TMEM_COLS>(tmem_base);
 }
 
 // out (C x R, pitch ldo) = in (R x C, pitch ldi)^T
@@ -327,19 +377,22 @@ size_t gemm_tc_workspace_bytes(int transA, int transB, int M, int N, int K) {
 
 static bool tc_eligible(int M, int N, int K) { return K >= 32 && M >= 32 && N >= 16 && (long long)M * N * K >= (1 << 18); }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int NMB, int STG>
 static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, float alpha, float beta,
-                          float* C, int ldc, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<A_MN, B_MN>;
+                          float* C, int ldc, int mn3d, int splits, cudaStream_t st) {
+  using G = gtc::Cfg<NMB, STG>;
+  auto kern = gemm_tc_kernel<A_MN, B_MN, NMB, STG>;
   static bool attr_set = false;
   if (!attr_set) {
-    DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gtc::SMEM_BYTES));
+    DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
     attr_set = true;
   }
   const MnCfg mc = mn_cfg_from_env();
   const unsigned int mn_cfg = (unsigned)(mc.layout & 7) | ((unsigned)(mc.lbo >> 4) << 4) | ((unsigned)(mc.sbo >> 4) << 18);
-  dim3 grid(cdiv(N, gtc::BN), cdiv(M, gtc::BM));
-  DS2_LAUNCH(kern, grid, gtc::THREADS, gtc::SMEM_BYTES, st, tmA, tmB, M, N, K, alpha, beta, C, ldc, mn_cfg);
+  if (splits > 1 && beta == 0.f)
+    DS2_CHECK_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
+  dim3 grid(cdiv(N, gtc::BN), cdiv(M, G::BM), splits);
+  DS2_LAUNCH(kern, grid, gtc::THREADS, G::SMEM_BYTES, st, tmA, tmB, M, N, K, alpha, beta, C, ldc, mn_cfg, mn3d);
   return DS2_OK;
 }
 
@@ -378,17 +431,49 @@ int gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const floa
   }
   if ((ldak & 3) || (ldbk & 3) || (reinterpret_cast<uintptr_t>(Ak) & 15) || (reinterpret_cast<uintptr_t>(Bk) & 15))
     return 1;
+  // tile configuration (DS2_GEMM_CFG: 0 auto, 1 = 128x256 / 4 stages, 2 = 256x256 / 3 stages, 3 = 128x256 / 2 stages
+  // with two CTAs per SM): 256 x 256 when that still fills the machine, if necessary with a 2-way split of K
+  int cfg = 1, splits = 1;
+  {
+    const char* e = getenv("DS2_GEMM_CFG");
+    const int forced = e ? atoi(e) : 0;
+    const long long tiles2 = (long long)cdiv(M, 256) * cdiv(N, gtc::BN);
+    if (forced >= 1 && forced <= 3) {
+      cfg = (forced == 2 && M < 256) ? 1 : forced;
+    } else if (M >= 256) {
+      if (tiles2 >= 120) cfg = 2;
+      else if (tiles2 * 2 >= 100 && tiles2 * 2 <= 148 && K >= 2048 && (beta == 0.f || beta == 1.f)) { cfg = 2; splits = 2; }
+    }
+  }
+  const int bm = cfg == 2 ? 256 : 128;
   CUtensorMap tmA, tmB;
-  // K-major: matrix [rows, K] box (32 k, rows) ; MN-major: matrix [K, rows] box (32 rows, 32 k)
+  // K-major: matrix [rows, K] box (32 k, rows).  MN-major: matrix [K, rows]: one 3-D box (32 rows, 32 k, blocks)
+  // when rows % 32 == 0, else 2-D boxes (32 rows, 32 k)
   const CUtensorMapSwizzle mn_sw = (CUtensorMapSwizzle)mn_cfg_from_env().sw;
-  int rc = a_mn ? make_tmap_2d_sw(&tmA, Ak, K, M, ldak, 32, 32, mn_sw) : make_tmap_2d(&tmA, Ak, M, K, ldak, gtc::BM, gtc::BK);
+  int mn3d = 0, rc;
+  if (a_mn && M % 32 == 0) {
+    mn3d |= 1;
+    rc = make_tmap_3d_sw(&tmA, Ak, 32, K, M / 32, (size_t)ldak, 32, 32, 32, bm / 32, mn_sw);
+  } else {
+    rc = a_mn ? make_tmap_2d_sw(&tmA, Ak, K, M, ldak, 32, 32, mn_sw) : make_tmap_2d(&tmA, Ak, M, K, ldak, bm, gtc::BK);
+  }
   if (rc) return rc;
-  rc = b_mn ? make_tmap_2d_sw(&tmB, Bk, K, N, ldbk, 32, 32, mn_sw) : make_tmap_2d(&tmB, Bk, N, K, ldbk, gtc::BN, gtc::BK);
+  if (b_mn && N % 32 == 0) {
+    mn3d |= 2;
+    rc = make_tmap_3d_sw(&tmB, Bk, 32, K, N / 32, (size_t)ldbk, 32, 32, 32, gtc::BN / 32, mn_sw);
+  } else {
+    rc = b_mn ? make_tmap_2d_sw(&tmB, Bk, K, N, ldbk, 32, 32, mn_sw) : make_tmap_2d(&tmB, Bk, N, K, ldbk, gtc::BN, gtc::BK);
+  }
   if (rc) return rc;
-  if (a_mn && b_mn) return launch_gemm_tc<true, true>(tmA, tmB, M, N, K, alpha, beta, C, ldc, st);
-  if (a_mn) return launch_gemm_tc<true, false>(tmA, tmB, M, N, K, alpha, beta, C, ldc, st);
-  if (b_mn) return launch_gemm_tc<false, true>(tmA, tmB, M, N, K, alpha, beta, C, ldc, st);
-  return launch_gemm_tc<false, false>(tmA, tmB, M, N, K, alpha, beta, C, ldc, st);
+#define DS2_GEMM_DISPATCH(AM, BMN)                                                                                   \
+  return cfg == 2   ? launch_gemm_tc<AM, BMN, 2, 3>(tmA, tmB, M, N, K, alpha, beta, C, ldc, mn3d, splits, st)        \
+         : cfg == 3 ? launch_gemm_tc<AM, BMN, 1, 2>(tmA, tmB, M, N, K, alpha, beta, C, ldc, mn3d, splits, st)        \
+                    : launch_gemm_tc<AM, BMN, 1, 4>(tmA, tmB, M, N, K, alpha, beta, C, ldc, mn3d, splits, st)
+  if (a_mn && b_mn) { DS2_GEMM_DISPATCH(true, true); }
+  if (a_mn) { DS2_GEMM_DISPATCH(true, false); }
+  if (b_mn) { DS2_GEMM_DISPATCH(false, true); }
+  DS2_GEMM_DISPATCH(false, false);
+#undef DS2_GEMM_DISPATCH
 }
 
 }  // namespace ds2

@@ -31,7 +31,7 @@ def timing(tA, tB, M, N, K, iters=10):
 
 def main():
     # tma_swizzle (3 = 128B, 4 = 128B_ATOM_32B), descriptor layout type, LBO, SBO
-    for cfg in ("4,1,4096,512", "4,1,512,4096", "4,1,4096,1024", "3,1,4096,512"):
+    for cfg in ("4,1,4096,512",):
         os.environ["DS2_GEMM_MN_MAJOR"] = "1"
         os.environ["DS2_GEMM_MN_CFG"] = cfg
         print("=== DS2_GEMM_MN_CFG", cfg, flush=True)
@@ -42,12 +42,21 @@ def main():
             except Exception:
                 print("[EXC]", args, traceback.format_exc(), flush=True)
     del os.environ["DS2_GEMM_MN_CFG"]
-    for on in ("0", "1"):
-        os.environ["DS2_GEMM_MN_MAJOR"] = on
-        print("=== timing DS2_GEMM_MN_MAJOR", on, flush=True)
+    os.environ["DS2_GEMM_MN_MAJOR"] = "1"
+    for args in [(1, 0, 4096, 1024, 16000), (0, 0, 16000, 1024, 4096), (0, 1, 16000, 4096, 1024), (1, 0, 4064, 1000, 15990),
+                 (0, 1, 1000, 520, 300), (1, 1, 4096, 1024, 4100)]:
+        try:
+            one(*args)
+        except Exception:
+            print("[EXC]", args, traceback.format_exc(), flush=True)
+    for cfg in ("1", "2", "3", "0"):
+        os.environ["DS2_GEMM_CFG"] = cfg
+        print("=== timing DS2_GEMM_CFG", cfg, "(1: 128x256x4st, 2: 256x256x3st, 3: 128x256x2st 2 CTA/SM, 0: auto)", flush=True)
         timing(1, 0, 4096, 1024, 16000)    # dW = dG^T . X
         timing(0, 0, 16000, 1024, 4096)    # dX = dG . W
-        timing(0, 1, 16000, 4096, 1024)    # projection (K-major both: control)
+        timing(0, 1, 16000, 4096, 1024)    # projection
+        timing(0, 1, 16000, 8192, 1312)
+    del os.environ["DS2_GEMM_CFG"]
 
 
 if __name__ == "__main__":
