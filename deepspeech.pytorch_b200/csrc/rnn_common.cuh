@@ -18,6 +18,12 @@ struct SeqArgs {
   const float* dy;        // bwd: (T,B,H)
   float* carry;           // bwd: (D,B,H) dc (LSTM) / dh (GRU)
   int training;
+  // bwd, optional: bias gradients accumulated inside the sweep (column sums of the gate gradients over (t,b)).
+  // dbias[d]: (G*H) zeroed by the caller; dbias_hn[d]: GRU only, (H) sum of the h-side n-gate gradient.
+  // The sweep sets *dbias_done = 1 when it filled them (otherwise the caller runs the column-sum kernels).
+  float* dbias[2];
+  float* dbias_hn[2];
+  int* dbias_done;
 };
 
 }  // namespace ds2

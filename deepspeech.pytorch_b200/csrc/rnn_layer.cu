@@ -390,6 +390,16 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
   a.gates = R.gates; a.hseq = R.hseq; a.aux = R.aux;
   for (int dir = 0; dir < D; ++dir) { a.w_hh[dir] = wT[dir]; a.b_ih[dir] = b_ih[dir]; a.b_hh[dir] = b_hh[dir]; }
   a.dy = dy; a.carry = carry; a.training = 1;
+  // bias gradients are column sums of the gate gradients: the tensor-core sweep can accumulate them on the fly
+  int dbias_done = 0;
+  const bool gru_l = d->rnn_type == DS2_RNN_GRU;
+  for (int dir = 0; dir < D; ++dir) {
+    a.dbias[dir] = db_ih[dir];
+    a.dbias_hn[dir] = gru_l ? db_hh[dir] + 2 * H : nullptr;
+    DS2_CHECK_CUDA(cudaMemsetAsync(db_ih[dir], 0, sizeof(float) * GH, st));
+    if (gru_l) DS2_CHECK_CUDA(cudaMemsetAsync(db_hh[dir] + 2 * H, 0, sizeof(float) * H, st));
+  }
+  a.dbias_done = &dbias_done;
   {
     DS2_PROF("rnn_bwd_sweep", st);
     rc = 1;
@@ -416,8 +426,10 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
     // dW_ih = dGx^T . xin
     rc = ds2_gemm(1, 0, GH, In, TB, 1.f, dG, ldg, xin, In, 0.f, dw_ih[dir], In, gws, gws_bytes, stream);
     if (rc) return rc;
-    rc = colsum(TB, GH, dG, ldg, db_ih[dir], st);
-    if (rc) return rc;
+    if (!dbias_done) {
+      rc = colsum(TB, GH, dG, ldg, db_ih[dir], st);
+      if (rc) return rc;
+    }
     // dW_hh = sum_t dGh[t]^T . h_prev[t]; h_prev[t] = hseq[t-1] (forward) / hseq[t+1] (reverse)
     const int Kr = (T - 1) * B;
     const size_t a_off = dir == 0 ? (size_t)B : 0, h_off = dir == 0 ? 0 : (size_t)B;
@@ -436,8 +448,10 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
     }
     if (gru) {
       DS2_CHECK_CUDA(cudaMemcpyAsync(db_hh[dir], db_ih[dir], sizeof(float) * 2 * H, cudaMemcpyDeviceToDevice, st));
-      rc = colsum(TB, H, aux_d, H, db_hh[dir] + 2 * H, st);
-      if (rc) return rc;
+      if (!dbias_done) {
+        rc = colsum(TB, H, aux_d, H, db_hh[dir] + 2 * H, st);
+        if (rc) return rc;
+      }
     } else {
       DS2_CHECK_CUDA(cudaMemcpyAsync(db_hh[dir], db_ih[dir], sizeof(float) * GH, cudaMemcpyDeviceToDevice, st));
     }

@@ -63,6 +63,8 @@ struct PersistParams {
   int defer;            // 1: stores that only later kernels read are issued after the barrier arrival
   int d0;               // first direction handled by this launch (directions can be launched one at a time
                         // when both together would not be co-resident, e.g. H = 1536)
+  float* dbias[2];      // split-K bwd: bias-gradient accumulators (G*H per direction, zeroed by the host) or null
+  float* dbias_hn[2];   // split-K bwd, GRU: sum of dGh_n (H per direction)
   int* err;             // set to 1 if a barrier wait timed out
 };
 
@@ -1161,6 +1163,12 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
     const uint32_t part_tx = (uint32_t)(4 * UT * NB * 4);                // bytes this CTA receives per step
     // resident: s_cur scales what this step writes, s_prev un-scales what this step's MMAs consumed
     const unsigned int* gmax_d = RES ? p.gmax + (size_t)d * (T + 1) : nullptr;
+    // bias gradients: this thread's 4 units x (gate) sums over all steps of its batch column(s)
+    float bsum[5][4];
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bsum[i][j] = 0.f;
     int sx_prev = 0, sx_cur = 0;
     if (RES) sx_cur = pow2_exp_for(ld_acquire(gmax_d), 0);
     float s_cur = pow2f(sx_cur), inv_prev = 1.f;
@@ -1344,6 +1352,10 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
         *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
       };
       auto store_dg = [&](int b, const float (&o)[5][NPF]) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+          for (int j = 0; j < NPF; ++j) bsum[i][j] += o[i][j];
         float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + uq;
 #pragma unroll
         for (int g = 0; g < G; ++g) st4(gp + g * H, o[g]);
@@ -1384,6 +1396,25 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
       if (defer) {
         if (b_own < B) store_dg(b_own, sv);
         if (e == 0) trace_stamp(p.trace, p.T, step, 13);
+      }
+    }
+    if (p.dbias[d]) {
+      // lanes with equal (lane & 3) hold the same 4 units for different batch columns: reduce over lane bits 2..4,
+      // then one atomic per (gate, unit) and warp
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        if (i >= G && !(RNN == DS2_RNN_GRU && i == 4)) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v = bsum[i][j];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (lane < 4) {
+            if (i < G) atomicAdd(&p.dbias[d][(size_t)i * H + u0 + 4 * lane + j], v);
+            else atomicAdd(&p.dbias_hn[d][u0 + 4 * lane + j], v);
+          }
+        }
       }
     }
   }
@@ -1439,6 +1470,7 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
   p.len = a.len; p.gates = a.gates; p.hseq = a.hseq; p.aux = a.aux; p.dy = a.dy;
   p.trace = trace_ptr_from_env("DS2_TRACE_BWD");
   p.defer = sweep_defer_default();
+  for (int d = 0; d < a.D; ++d) { p.dbias[d] = a.dbias[d]; p.dbias_hn[d] = a.dbias_hn[d]; }
   set_acc_layout(p);
   char* base = static_cast<char*>(ws);
   p.err = reinterpret_cast<int*>(base);
@@ -1508,6 +1540,7 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
+  if (a.dbias_done && a.dbias[0]) *a.dbias_done = 1;
   return DS2_OK;
 }
 
