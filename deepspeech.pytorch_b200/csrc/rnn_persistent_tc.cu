@@ -976,22 +976,25 @@ __device__ __forceinline__ int pow2_exp_for(unsigned int m_bits, int sx_prev) {
 }
 __device__ __forceinline__ float pow2f(int ex) { return __int_as_float((ex + 127) << 23); }   // |ex| <= 100
 
-template <int RNN, bool RES>
+// CL = CTAs per cluster = K split: 4 (64 units per cluster, MMA M = 64) or 8 (128 units, M = 128: the same
+// number of CTAs, but each reduces only K/8, i.e. half as many MMA instructions on the per-step critical path).
+template <int RNN, bool RES, int CL>
 __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __grid_constant__ PersistParams p) {
   using namespace rp;
   using namespace tc;
   constexpr int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
-  constexpr int UM = 64;                       // units per cluster (all M rows valid)
+  constexpr int UM = UT * CL;                  // units per cluster (all M rows valid): 64 or 128 = MMA M
+  constexpr int A_BYTES = UM * 128;            // one K chunk of the weight tile (shadows rp::A_BYTES)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB aligned, still __shared__
   const int NB = p.NB, B = p.B, T = p.T, H = p.H, D = p.D;
   const int B_BYTES = NB * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   const int NBp = NB + 1;
-  const int NKR = (G * H / 4) / 64;                                      // resident: 64 fp16 of K per chunk
+  const int NKR = (G * H / CL) / 64;                                     // resident: 64 fp16 of K per chunk
   const int NG = grp_count(NKR);
   const int ring_bytes = RES ? NKR * STAGE_BYTES : STAGES * STAGE_BYTES;
   const int PS = ((NB + 3) & ~3) + 4;                                    // row pitch of the received tiles (16 B aligned)
-  float* part = reinterpret_cast<float*>(smem + ring_bytes);             // [4 sources][16][PS] partial dh_rec
+  float* part = reinterpret_cast<float*>(smem + ring_bytes);             // [CL sources][16][PS] partial dh_rec
   float* cst = part + UM * PS;                                           // [16][NBp] carried dc / dh
   int* lens_s = reinterpret_cast<int*>(cst + UT * NBp);
   unsigned int* cta_max = reinterpret_cast<unsigned int*>(lens_s + ((NB + 1) & ~1));   // [2] (8 bytes)
@@ -1002,16 +1005,16 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(part_bar + 1);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int ks = blockIdx.x & 3;                          // rank in the cluster == K split
-  const int cl = blockIdx.x >> 2;
+  const int ks = blockIdx.x % CL;                         // rank in the cluster == K split
+  const int cl = blockIdx.x / CL;
   const int NTc = H / UM;                                 // clusters per direction
   const int d = p.d0 + cl / NTc, ut = cl % NTc;
   const int GH = G * H;
-  const int Kc = GH / 4, NK = Kc / BK;
+  const int Kc = GH / CL, NK = Kc / BK;
   const int kbase = ks * Kc;
   const int u0 = ut * UM + ks * UT;                       // the 16 units this CTA finishes
   unsigned int* ctr = p.bar + 32 * d;
-  const unsigned int n_arrive = (unsigned int)(NTc * 4);
+  const unsigned int n_arrive = (unsigned int)(NTc * CL);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmW[d]);
@@ -1101,7 +1104,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
   } else if (warp == 1) {
     if (RES) {
       if (lane == 0) {
-        const uint32_t idesc = instr_desc(FMT_F16, MM, NB);
+        const uint32_t idesc = instr_desc(FMT_F16, UM, NB);
         const uint64_t a_base = smem_desc_sw128(smem_u32(smem));
         const uint64_t b_base = smem_desc_sw128(smem_u32(smem + NKR * A_BYTES));
         const uint64_t a_step = (uint64_t)(A_BYTES >> 4), b_step = (uint64_t)(B_BYTES >> 4);
@@ -1129,7 +1132,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
       }
     } else
     if (lane == 0) {
-      const uint32_t idesc = instr_desc(FMT_TF32, MM, NB);
+      const uint32_t idesc = instr_desc(FMT_TF32, UM, NB);
       const uint64_t a_base = smem_desc_sw128(smem_u32(smem));
       const uint64_t b_base = smem_desc_sw128(smem_u32(smem + A_BYTES));
       const uint64_t stage_step = (uint64_t)(STAGE_BYTES >> 4);
@@ -1157,10 +1160,14 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
     const int e = threadIdx.x - 64;
     const int ul = lane & 15, half = lane >> 4;
     uint32_t acc_phase = 0, part_phase = 0;
-    // destination of this warp's TMEM quarter: CTA q of the cluster, slice ks (= this CTA's rank) of its tile
-    const uint32_t dst_row = mapa_u32(smem_u32(part), (uint32_t)q) + (uint32_t)((ks * UT + ul) * PS * 4);
-    const uint32_t dst_bar = mapa_u32(smem_u32(part_bar), (uint32_t)q);
-    const uint32_t part_tx = (uint32_t)(4 * UT * NB * 4);                // bytes this CTA receives per step
+    // Destination of this lane's accumulator row: the CTA that finishes the row's unit, slice ks (= this CTA's rank)
+    // of its tile.  M = 64 (CL 4): TMEM quarter q holds rows 16q..16q+15 in lanes 0..15 -> CTA q, the 32 columns are
+    // split with lane+16 by shuffle.  M = 128 (CL 8): lane l of quarter q holds row 32q+l -> CTA 2q + l/16, all 32
+    // columns of the row are sent by that lane.
+    const int dst_cta = CL == 4 ? q : 2 * q + half;
+    const uint32_t dst_row = mapa_u32(smem_u32(part), (uint32_t)dst_cta) + (uint32_t)((ks * UT + ul) * PS * 4);
+    const uint32_t dst_bar = mapa_u32(smem_u32(part_bar), (uint32_t)dst_cta);
+    const uint32_t part_tx = (uint32_t)(CL * UT * NB * 4);               // bytes this CTA receives per step
     // resident: s_cur scales what this step writes, s_prev un-scales what this step's MMAs consumed
     const unsigned int* gmax_d = RES ? p.gmax + (size_t)d * (T + 1) : nullptr;
     // bias gradients: this thread's 4 units x (gate) sums over all steps of its batch column(s)
@@ -1259,22 +1266,30 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
         for (int cb = 0; cb < NB; cb += 32) {
           float acc[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, acc);
-          float v[16];
+          if (CL == 4) {
+            float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float hi = __shfl_sync(0xffffffffu, acc[16 + j], ul);
-            v[j] = half ? hi : acc[j];
-          }
+            for (int j = 0; j < 16; ++j) {
+              const float hi = __shfl_sync(0xffffffffu, acc[16 + j], ul);
+              v[j] = half ? hi : acc[j];
+            }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c0 = cb + half * 16 + 4 * i;        // NB is a multiple of 8: a group of 4 columns is in or out
-            if (c0 < NB) st_async_v4(dst_row + (uint32_t)(c0 * 4), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], dst_bar);
+            for (int i = 0; i < 4; ++i) {
+              const int c0 = cb + half * 16 + 4 * i;      // NB is a multiple of 8: a group of 4 columns is in or out
+              if (c0 < NB) st_async_v4(dst_row + (uint32_t)(c0 * 4), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], dst_bar);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int c0 = cb + 4 * i;
+              if (c0 < NB) st_async_v4(dst_row + (uint32_t)(c0 * 4), acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3], dst_bar);
+            }
           }
         }
         acc_phase ^= 1;
         tc_fence_before();
         if (e == 0) trace_stamp(p.trace, p.T, step, 6);
-        mbar_wait_cluster(part_bar, part_phase, p.err);   // all four slices of this CTA's units have landed
+        mbar_wait_cluster(part_bar, part_phase, p.err);   // all CL slices of this CTA's units have landed
         part_phase ^= 1;
       }
       if (e == 0) trace_stamp(p.trace, p.T, step, 7);
@@ -1310,6 +1325,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
           if (step > 0) {
             const float* pr = part + (uq + j) * PS + b;
             rec = (pr[0] + pr[UT * PS]) + (pr[2 * UT * PS] + pr[3 * UT * PS]);
+            if (CL == 8) rec += (pr[4 * UT * PS] + pr[5 * UT * PS]) + (pr[6 * UT * PS] + pr[7 * UT * PS]);
           }
           dh[j] = dyv[j] + (RES ? rec * inv_prev : rec);
         }
@@ -1424,12 +1440,12 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-static size_t splitk_smem_bytes(int NB) {
+static size_t splitk_smem_bytes(int NB, int CL) {
   using namespace rp;
   size_t NBp = NB + 1;
   size_t PS = ((NB + 3) & ~3) + 4;
-  return 1024 + (size_t)STAGES * (A_BYTES + (size_t)NB * 128) + (64 * PS + UT * NBp + NB + 8) * sizeof(float) +
-         (2 * STAGES + 3) * sizeof(uint64_t) + 64;
+  return 1024 + (size_t)STAGES * ((size_t)UT * CL * 128 + (size_t)NB * 128) +
+         ((size_t)UT * CL * PS + UT * NBp + NB + 8) * sizeof(float) + (2 * STAGES + 3) * sizeof(uint64_t) + 64;
 }
 
 // max |x| over n floats -> atomicMax on float bits (x >= 0 after fabs)
@@ -1442,12 +1458,12 @@ __global__ void absmax_kernel(size_t n, const float* __restrict__ x, unsigned in
   if (threadIdx.x % 32 == 0) atomicMax(out, __float_as_uint(m));
 }
 
-static size_t splitk_res_smem_bytes(int NB, int Kc) {
+static size_t splitk_res_smem_bytes(int NB, int Kc, int CL) {
   using namespace rp;
   size_t NBp = NB + 1;
   size_t PS = ((NB + 3) & ~3) + 4;
-  return 1024 + (size_t)(Kc / 64) * (A_BYTES + (size_t)NB * 128) + (64 * PS + UT * NBp + NB + 8) * sizeof(float) +
-         (32 + STAGES + 3) * sizeof(uint64_t) + 64;
+  return 1024 + (size_t)(Kc / 64) * ((size_t)UT * CL * 128 + (size_t)NB * 128) +
+         ((size_t)UT * CL * PS + UT * NBp + NB + 8) * sizeof(float) + (32 + STAGES + 3) * sizeof(uint64_t) + 64;
 }
 // workspace of the resident backward: [4 KB control][gmax D*(T+1) uints][W^T fp16: D*H*GH][dg16: T*B*D*GH]
 static size_t splitk_res_ws_bytes(int G, int T, int B, int H, int D) {
@@ -1456,16 +1472,17 @@ static size_t splitk_res_ws_bytes(int G, int T, int B, int H, int D) {
          align_up((size_t)T * B * D * GH * 2, 256);
 }
 
-template <int RNN>
+template <int RNN, int CL>
 static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
   using namespace rp;
   const int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
   const int GH = G * a.H;
-  if (a.H % 64 != 0 || GH % 4 != 0 || (GH / 4) % 64 != 0 || (GH / 4) / 64 > 120) return 1;   // <= 32 group barriers
+  constexpr int UM = UT * CL;
+  if (a.H % UM != 0 || GH % CL != 0 || (GH / CL) % 64 != 0 || (GH / CL) / 64 > 120) return 1;   // <= 32 group barriers
   if (!vec_ok(a.gates, a.hseq, a.aux, a.dy)) return 1;
   if (ws_bytes < splitk_res_ws_bytes(G, a.T, a.B, a.H, a.D)) return 1;
   PersistParams p{};
-  p.T = a.T; p.B = a.B; p.NB = (a.B + 7) / 8 * 8; p.H = a.H; p.D = a.D; p.NT = a.H / 64; p.G = G;
+  p.T = a.T; p.B = a.B; p.NB = (a.B + 7) / 8 * 8; p.H = a.H; p.D = a.D; p.NT = a.H / UM; p.G = G;
   p.training = 1;
   p.len = a.len; p.gates = a.gates; p.hseq = a.hseq; p.aux = a.aux; p.dy = a.dy;
   p.trace = trace_ptr_from_env("DS2_TRACE_BWD");
@@ -1479,15 +1496,15 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
   p.gmax = reinterpret_cast<unsigned int*>(base + off); off += align_up((size_t)a.D * (a.T + 1) * 4, 256);
   __half* wT16 = reinterpret_cast<__half*>(base + off); off += align_up((size_t)a.D * a.H * GH * 2, 256);
   p.dg16 = reinterpret_cast<__half*>(base + off);
-  const size_t smem = one_cta_per_sm(splitk_res_smem_bytes(p.NB, GH / 4));
+  const size_t smem = one_cta_per_sm(splitk_res_smem_bytes(p.NB, GH / CL, CL));
   if (smem > 227 * 1024) return 1;
-  auto kern = rnn_bwd_splitk_kernel<RNN, true>;
+  auto kern = rnn_bwd_splitk_kernel<RNN, true, CL>;
   static bool attr_done = false;
   if (!attr_done) {
     DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
-  int grid = a.D * p.NT * 4, launches = 1;
+  int grid = a.D * p.NT * CL, launches = 1;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(THREADS);
@@ -1495,7 +1512,7 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
   cfg.stream = st;
   cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
-  attrs[0].val.clusterDim.x = 4; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  attrs[0].val.clusterDim.x = CL; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
   attrs[1].id = cudaLaunchAttributeCooperative;
   attrs[1].val.cooperative = 1;
   cfg.attrs = attrs;
@@ -1505,9 +1522,11 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
   int max_clusters = 0;
   cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
   if (oe != cudaSuccess) { (void)cudaGetLastError(); return 1; }
-  if (max_clusters * 4 < grid) {
-    if (max_clusters * 4 < p.NT * 4) return 1;
-    grid = p.NT * 4;
+  if (max_clusters * CL < grid) {
+    // 8-CTA clusters are only worth it when both directions run concurrently (B200: 16 clusters of 8 do not fit the
+    // GPCs, measured: 10.4k cycles per step instead of 11.7k, but the two directions then run back to back)
+    if (CL == 8 || max_clusters * CL < p.NT * CL) return 1;
+    grid = p.NT * CL;
     launches = a.D;
     cfg.gridDim = dim3(grid);
   }
@@ -1515,11 +1534,11 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
   const size_t wn = (size_t)a.H * GH;
   for (int d = 0; d < a.D; ++d) {
     DS2_LAUNCH(f32_to_f16_kernel, 148 * 4, 256, 0, st, wn, a.w_hh[d], wT16 + (size_t)d * wn);
-    int rc = make_tmap_f16(&p.tmW[d], wT16 + (size_t)d * wn, 2, GH, a.H, 1, (size_t)GH, 0, 64, 64, 1);
+    int rc = make_tmap_f16(&p.tmW[d], wT16 + (size_t)d * wn, 2, GH, a.H, 1, (size_t)GH, 0, 64, UM, 1);
     if (rc) return rc;
     rc = make_tmap_f16(&p.tmV[d], p.dg16, 2, a.D * GH, a.T * a.B, 1, (size_t)a.D * GH, 0, 64, a.B, 1);
     if (rc) return rc;
-    p.box3 = ((GH / 4) / 64) % 4 == 0;
+    p.box3 = ((GH / CL) / 64) % 4 == 0;
     if (p.box3) {
       rc = make_tmap_f16(&p.tmV3[d], p.dg16, 3, 64, a.T * a.B, a.D * GH / 64, (size_t)a.D * GH, 64, 64, p.NB, 4);
       if (rc) return rc;
@@ -1544,19 +1563,20 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
   return DS2_OK;
 }
 
-template <int RNN>
+template <int RNN, int CL>
 static int launch_bwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
   using namespace rp;
   const int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
   const int GH = G * a.H;
   if (!getenv("DS2_NO_RESIDENT")) {
-    int rc = launch_bwd_splitk_resident<RNN>(a, ws, ws_bytes, st);
+    int rc = launch_bwd_splitk_resident<RNN, CL>(a, ws, ws_bytes, st);
     if (rc != 1) return rc;
   }
-  if (a.H % 64 != 0 || (GH / 4) % BK != 0 || GH % 4 != 0) return 1;
+  constexpr int UM = UT * CL;
+  if (a.H % UM != 0 || (GH / CL) % BK != 0 || GH % CL != 0) return 1;
   if (!vec_ok(a.gates, a.hseq, a.aux, a.dy)) return 1;
   PersistParams p{};
-  p.T = a.T; p.B = a.B; p.NB = (a.B + 7) / 8 * 8; p.H = a.H; p.D = a.D; p.NT = a.H / 64; p.G = G;
+  p.T = a.T; p.B = a.B; p.NB = (a.B + 7) / 8 * 8; p.H = a.H; p.D = a.D; p.NT = a.H / UM; p.G = G;
   p.training = 1;
   p.len = a.len; p.gates = a.gates; p.hseq = a.hseq; p.aux = a.aux; p.dy = a.dy;
   p.trace = trace_ptr_from_env("DS2_TRACE_BWD");
@@ -1564,15 +1584,15 @@ static int launch_bwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
   set_acc_layout(p);
   p.err = static_cast<int*>(ws);
   p.bar = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + 128);
-  const size_t smem = one_cta_per_sm(splitk_smem_bytes(p.NB));
+  const size_t smem = one_cta_per_sm(splitk_smem_bytes(p.NB, CL));
   if (smem > 227 * 1024) return 1;
-  auto kern = rnn_bwd_splitk_kernel<RNN, false>;
+  auto kern = rnn_bwd_splitk_kernel<RNN, false, CL>;
   static bool attr_done = false;
   if (!attr_done) {
     DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
-  int grid = a.D * p.NT * 4, launches = 1;
+  int grid = a.D * p.NT * CL, launches = 1;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(THREADS);
@@ -1580,7 +1600,7 @@ static int launch_bwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
   cfg.stream = st;
   cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
-  attrs[0].val.clusterDim.x = 4; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  attrs[0].val.clusterDim.x = CL; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
   attrs[1].id = cudaLaunchAttributeCooperative;
   attrs[1].val.cooperative = 1;
   cfg.attrs = attrs;
@@ -1590,14 +1610,14 @@ static int launch_bwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
   int max_clusters = 0;
   cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
   if (oe != cudaSuccess) { (void)cudaGetLastError(); return 1; }
-  if (max_clusters * 4 < grid) {                         // all clusters must be co-resident (grid barrier)
-    if (max_clusters * 4 < p.NT * 4) return 1;
-    grid = p.NT * 4;                                     // one launch per direction
+  if (max_clusters * CL < grid) {                        // all clusters must be co-resident (grid barrier)
+    if (CL == 8 || max_clusters * CL < p.NT * CL) return 1;
+    grid = p.NT * CL;                                    // one launch per direction
     launches = a.D;
     cfg.gridDim = dim3(grid);
   }
   for (int d = 0; d < a.D; ++d) {
-    int rc = make_tmap_2d(&p.tmW[d], a.w_hh[d], a.H, GH, GH, 64, BK);   // W_hh^T (H, G*H): 64 unit rows per box
+    int rc = make_tmap_2d(&p.tmW[d], a.w_hh[d], a.H, GH, GH, UM, BK);   // W_hh^T (H, G*H): UM unit rows per box
     if (rc) return rc;
     rc = make_tmap_2d(&p.tmV[d], a.gates, a.T * a.B, a.D * GH, a.D * GH, a.B, BK);
     if (rc) return rc;
@@ -1683,9 +1703,18 @@ int rnn_sweep_bwd_tc(int rnn, const SeqArgs& a, void* ws, size_t ws_bytes, cudaS
   {
     int rc = 1;
     if (!getenv("DS2_NO_SPLITK")) {
-      if (rnn == DS2_RNN_LSTM) rc = launch_bwd_splitk<DS2_RNN_LSTM>(a, ws, ws_bytes, st);
-      else if (rnn == DS2_RNN_GRU) rc = launch_bwd_splitk<DS2_RNN_GRU>(a, ws, ws_bytes, st);
-      else rc = launch_bwd_splitk<DS2_RNN_TANH>(a, ws, ws_bytes, st);
+      // 8-CTA clusters (128 units, K/8 per CTA) halve the MMA chain of a step; 4-CTA clusters take the shapes
+      // they do not (H % 128, K/8 not a multiple of 64, or 8-CTA clusters that do not fit the GPCs)
+      if (env_flag("DS2_SPLITK_CL", 8) == 8) {
+        if (rnn == DS2_RNN_LSTM) rc = launch_bwd_splitk<DS2_RNN_LSTM, 8>(a, ws, ws_bytes, st);
+        else if (rnn == DS2_RNN_GRU) rc = launch_bwd_splitk<DS2_RNN_GRU, 8>(a, ws, ws_bytes, st);
+        else rc = launch_bwd_splitk<DS2_RNN_TANH, 8>(a, ws, ws_bytes, st);
+      }
+      if (rc == 1) {
+        if (rnn == DS2_RNN_LSTM) rc = launch_bwd_splitk<DS2_RNN_LSTM, 4>(a, ws, ws_bytes, st);
+        else if (rnn == DS2_RNN_GRU) rc = launch_bwd_splitk<DS2_RNN_GRU, 4>(a, ws, ws_bytes, st);
+        else rc = launch_bwd_splitk<DS2_RNN_TANH, 4>(a, ws, ws_bytes, st);
+      }
     }
     if (rc != 1) return rc;   // done or a hard error; 1 = not eligible -> 16-unit kernel below
   }
