@@ -658,10 +658,17 @@ static int launch_fwd_resident(const SeqArgs& a, void* ws, size_t ws_bytes, cuda
 }
 
 template <int RNN>
+static int launch_fwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st);
+
+template <int RNN>
 static int launch_fwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
   using namespace rp;
   const int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
   if (!getenv("DS2_NO_RESIDENT")) {
+    if (RNN != DS2_RNN_TANH && env_flag("DS2_FWD_SPLITK", 1)) {   // 2-CTA clusters, half the MMA chain per step
+      int rc = launch_fwd_splitk<RNN == DS2_RNN_TANH ? DS2_RNN_LSTM : RNN>(a, ws, ws_bytes, st);
+      if (rc != 1) return rc;
+    }
     int rc = launch_fwd_resident<RNN>(a, ws, ws_bytes, st);
     if (rc != 1) return rc;
   }
@@ -1440,6 +1447,395 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Forward sweep, split-K variant (LSTM / GRU, resident fp16 weights).  A 2-CTA cluster owns 32 hidden units of
+// one direction; CTA `rank` multiplies the G*32 gate rows (MMA M = 128, rows ordered [owner CTA][gate][unit])
+// with its half of K = H, so a step issues H/32 MMAs instead of H/16 — the single-thread MMA issue chain is the
+// longest part of a step.  TMEM lanes 0..63 hold the rows CTA 0 finishes, lanes 64..127 those of CTA 1: every
+// epilogue warp pushes its 32 accumulator rows into the owner's shared memory with st.async (complete_tx on
+// the owner's mbarrier); the owner adds the two partial tiles, the input projection and the biases, and runs
+// gates + cell update for its 16 units in one pass (thread = 4 consecutive units x one batch column).
+template <int RNN>
+__global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __grid_constant__ PersistParams p) {
+  using namespace rp;
+  using namespace tc;
+  constexpr int G = RNN == DS2_RNN_LSTM ? 4 : 3;
+  constexpr int AW = 128 * 128;                          // bytes of one K chunk of the weight tile (128 rows)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB aligned, still __shared__
+  const int NB = p.NB, B = p.B, T = p.T, H = p.H, D = p.D;
+  const int B_BYTES = NB * 128;
+  const int NBp = NB + 1;
+  const int PS = ((NB + 3) & ~3) + 4;                    // row pitch of the received tiles (16 B aligned)
+  const int NKR = H / 128;                               // 64-wide fp16 chunks of this CTA's K half
+  const int NG = grp_count(NKR);
+  float* part = reinterpret_cast<float*>(smem + NKR * (AW + B_BYTES));   // [2 sources][64 rows][PS]
+  float* cst = part + 128 * PS;                                          // [16][NBp] cell (LSTM) / hidden (GRU) state
+  int* lens_s = reinterpret_cast<int*>(cst + UT * NBp);
+  uint64_t* full = reinterpret_cast<uint64_t*>(lens_s + ((NB + 1) & ~1));   // one per group of 4 chunks (<= 8)
+  uint64_t* wbar = full + 8;
+  uint64_t* accum_bar = wbar + 1;
+  uint64_t* part_bar = accum_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(part_bar + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int rank = blockIdx.x & 1, cl = blockIdx.x >> 1;
+  const int NTc = H / 32;                                // clusters per direction
+  const int d = p.d0 + cl / NTc, U0 = (cl % NTc) * 32;   // first unit of the cluster
+  const int u0 = U0 + rank * UT;                         // the 16 units this CTA finishes
+  const int GH = G * H;
+  unsigned int* ctr = p.bar + 32 * d;
+  const unsigned int n_arrive = (unsigned int)(NTc * 2);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmW[d]);
+    tma_prefetch_desc(&p.tmV[d]);
+    for (int i = 0; i < 8; ++i) mbar_init(&full[i], 1);
+    mbar_init(wbar, 1);
+    mbar_init(accum_bar, 1);
+    mbar_init(part_bar, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < UT * NBp; i += THREADS) cst[i] = 0.f;
+  for (int i = threadIdx.x; i < NB; i += THREADS) lens_s[i] = i < B ? p.len[i] : 0;
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_all();                                     // the peer's mbarriers are initialised
+  const uint32_t tmem_base = *tmem_slot;
+  if (tmem_base != 0 && threadIdx.x == 0) {               // literal TMEM address 0 in the MMAs, see the other kernels
+    *(volatile int*)p.err = 2;
+    printf("ds2: unexpected TMEM base %u (block %d)\n", tmem_base, blockIdx.x);
+  }
+  const int kc0 = rank * NKR;                             // first K chunk (of H/64) of this CTA
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // weights once: per chunk the rows of the two owners, [gate][16 units] each (rows >= 16 G of a half unused)
+      mbar_arrive_expect_tx(wbar, (uint32_t)(NKR * 2 * G * UT * 128));
+      for (int c = 0; c < NKR; ++c) {
+        tma_load_3d(smem + c * AW, &p.tmW[d], wbar, (kc0 + c) * 64, U0, 0);
+        tma_load_3d(smem + c * AW + 64 * 128, &p.tmW[d], wbar, (kc0 + c) * 64, U0 + UT, 0);
+      }
+      uint8_t* hbuf = smem + NKR * AW;
+      for (int step = 1; step < T; ++step) {
+        const int t = d == 0 ? step : T - 1 - step;
+        const int tp = d == 0 ? t - 1 : t + 1;
+        grid_wait_counter(ctr, n_arrive * (unsigned int)step, p.err);
+        fence_proxy_async_global();
+        trace_stamp(p.trace, p.T, step, 0);
+        for (int g = 0; g < NG; ++g) {
+          uint64_t* fb = full + g;
+          const int c0 = grp_begin(g), c1 = min(NKR, grp_begin(g + 1));
+          if (p.box3) {
+            mbar_arrive_expect_tx(fb, (uint32_t)(4 * B_BYTES));
+            tma_load_3d(hbuf + c0 * B_BYTES, &p.tmV3[d], fb, 0, tp * B, kc0 + c0);
+          } else {
+            mbar_arrive_expect_tx(fb, (uint32_t)((c1 - c0) * B * 128));
+            for (int c = c0; c < c1; ++c) tma_load_2d(hbuf + c * B_BYTES, &p.tmV[d], fb, (kc0 + c) * 64, tp * B);
+          }
+        }
+        trace_stamp(p.trace, p.T, step, 1);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(FMT_F16, 128, NB);
+      const uint64_t a_base = smem_desc_sw128(smem_u32(smem));
+      const uint64_t b_base = smem_desc_sw128(smem_u32(smem + NKR * AW));
+      const uint64_t a_step = (uint64_t)(AW >> 4), b_step = (uint64_t)(B_BYTES >> 4);
+      mbar_wait(wbar, 0);
+      uint32_t ph = 0;
+      for (int step = 1; step < T; ++step) {
+        for (int g = 0; g < NG; ++g) {
+          mbar_wait(full + g, ph);
+          tc_fence_after();
+          if (g == 0) trace_stamp(p.trace, p.T, step, 2);
+          const int c0 = grp_begin(g), c1 = min(NKR, grp_begin(g + 1));
+          if (c1 == NKR) trace_stamp(p.trace, p.T, step, 3);
+          for (int c = c0; c < c1; ++c) {
+            const uint64_t ad = a_base + (uint64_t)c * a_step, bd = b_base + (uint64_t)c * b_step;
+            mma_f16(0u, ad, bd, idesc, c > 0);
+            mma_f16(0u, ad + 2, bd + 2, idesc, 1);
+            mma_f16(0u, ad + 4, bd + 4, idesc, 1);
+            mma_f16(0u, ad + 6, bd + 6, idesc, 1);
+          }
+        }
+        mma_commit(accum_bar);
+        trace_stamp(p.trace, p.T, step, 4);
+        ph ^= 1;
+      }
+    }
+  } else {
+    const int q = warp % 4;
+    const int e = threadIdx.x - 64;          // 0..127
+    // TMEM lane (= row) 32q + lane belongs to CTA q/2; inside that CTA's 64-row slice it is row 32 (q&1) + lane
+    const int dst_cta = q >> 1;
+    const uint32_t dst_row = mapa_u32(smem_u32(part), (uint32_t)dst_cta) +
+                             (uint32_t)((rank * 64 + 32 * (q & 1) + lane) * PS * 4);
+    const uint32_t dst_bar = mapa_u32(smem_u32(part_bar), (uint32_t)dst_cta);
+    const uint32_t part_tx = (uint32_t)(2 * 64 * NB * 4);
+    const int uq = 4 * (e & 3), b_own = e >> 2;
+    // biases of this thread's 4 units: x-side + h-side summed, except the GRU n gate (r multiplies the h side)
+    float bsum[G][4], bhn[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float bx = p.b_ih[d][g * H + u0 + uq + j], bh = p.b_hh[d][g * H + u0 + uq + j];
+        bsum[g][j] = (RNN == DS2_RNN_GRU && g == 2) ? bx : bx + bh;
+        if (RNN == DS2_RNN_GRU && g == 2) bhn[j] = bh;
+      }
+      if (RNN != DS2_RNN_GRU) bhn[j] = 0.f;
+    }
+    auto ld4 = [](const float* src, float (&v)[4]) {
+      const float4 x = *reinterpret_cast<const float4*>(src);
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+    };
+    auto st4 = [](float* dst, const float (&v)[4]) { *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]); };
+    uint32_t acc_phase = 0, part_phase = 0;
+    const bool single = B <= 32;
+    for (int step = 0; step < T; ++step) {
+      const int t = d == 0 ? step : T - 1 - step;
+      // input projections of this thread's cells: independent of the recurrence, fetched before the MMA wait
+      float gx[G][4];
+      if (single && b_own < B) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) ld4(p.gates + (((size_t)t * B + b_own) * D + d) * GH + (size_t)g * H + u0 + uq, gx[g]);
+      }
+      if (step > 0) {
+        if (e == 0) mbar_arrive_expect_tx(part_bar, part_tx);   // arm this step's phase (the peer may already have sent)
+        mbar_wait(accum_bar, acc_phase);
+        tc_fence_after();
+        if (e == 0) trace_stamp(p.trace, p.T, step, 5);
+        for (int cb = 0; cb < NB; cb += 32) {
+          float acc[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, acc);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int c0 = cb + 4 * i;                    // NB is a multiple of 8: a group of 4 columns is in or out
+            if (c0 < NB) st_async_v4(dst_row + (uint32_t)(c0 * 4), acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3], dst_bar);
+          }
+        }
+        acc_phase ^= 1;
+        tc_fence_before();
+        if (e == 0) trace_stamp(p.trace, p.T, step, 6);
+        mbar_wait_cluster(part_bar, part_phase, p.err);   // both partial tiles of this CTA's rows have landed
+        part_phase ^= 1;
+      }
+      if (e == 0) trace_stamp(p.trace, p.T, step, 7);
+      // ---- gates + cell update: o[0..G-1] saved gate values, o[4] aux (LSTM c / GRU h_n + b_hn), o[5] h
+      auto cell4 = [&](int b, const float (&x)[G][4], float (&o)[6][4]) {
+        const bool valid = t < lens_s[b];
+        float pre[G][4], hn[4], hval[4];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float r = 0.f;
+            if (step > 0) {
+              const float* pr = part + (g * UT + uq + j) * PS + b;
+              r = pr[0] + pr[64 * PS];
+            }
+            if (RNN == DS2_RNN_GRU && g == 2) { hn[j] = r + bhn[j]; pre[g][j] = x[g][j] + bsum[g][j]; }
+            else pre[g][j] = (x[g][j] + r) + bsum[g][j];
+          }
+        if (RNN == DS2_RNN_LSTM) {
+          float a[4][4], cval[4], th[4];
+          // i, f, o: sigmoid; g: tanh = 2 sigmoid(2x) - 1  (one EX2 + one RCP per value, stage by stage)
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[g][j] = ex2_ftz((g == 2 ? -2.f * LOG2E : -LOG2E) * pre[g][j]);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[g][j] = rcp_ftz(1.f + a[g][j]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            a[2][j] = fmaf(2.f, a[2][j], -1.f);
+            cval[j] = valid ? fmaf(a[1][j], cst[(uq + j) * NBp + b], a[0][j] * a[2][j]) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) th[j] = ex2_ftz(-2.f * LOG2E * cval[j]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) th[j] = rcp_ftz(1.f + th[j]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            hval[j] = valid ? a[3][j] * fmaf(2.f, th[j], -1.f) : 0.f;
+            if (valid) cst[(uq + j) * NBp + b] = cval[j];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) o[g][j] = valid ? a[g][j] : 0.f;
+            o[4][j] = cval[j];
+          }
+        } else {
+          float a[2][4], nv[4];
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[g][j] = ex2_ftz(-LOG2E * pre[g][j]);
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[g][j] = rcp_ftz(1.f + a[g][j]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) nv[j] = ex2_ftz(-2.f * LOG2E * fmaf(a[0][j], hn[j], pre[2][j]));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) nv[j] = rcp_ftz(1.f + nv[j]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float nval = valid ? fmaf(2.f, nv[j], -1.f) : 0.f;
+            const float hprev = cst[(uq + j) * NBp + b];
+            hval[j] = valid ? fmaf(a[1][j], hprev - nval, nval) : 0.f;
+            if (valid) cst[(uq + j) * NBp + b] = hval[j];
+            o[0][j] = valid ? a[0][j] : 0.f; o[1][j] = valid ? a[1][j] : 0.f; o[2][j] = nval; o[3][j] = 0.f;
+            o[4][j] = valid ? hn[j] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[5][j] = hval[j];
+        const __half2 lo = __floats2half2_rn(hval[0], hval[1]), hi = __floats2half2_rn(hval[2], hval[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const unsigned int*>(&lo);
+        pk.y = *reinterpret_cast<const unsigned int*>(&hi);
+        *reinterpret_cast<uint2*>(p.h16 + (((size_t)d * T + t) * B + b) * H + u0 + uq) = pk;
+      };
+      auto store4 = [&](int b, const float (&o)[6][4]) {
+        const size_t so = (((size_t)d * T + t) * B + b) * H + u0 + uq;
+        float* gp = p.gates + (((size_t)t * B + b) * D + d) * GH + u0 + uq;
+        st4(p.aux + so, o[4]);
+        if (p.training) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) st4(gp + g * H, o[g]);
+        }
+        st4(p.hseq + so, o[5]);
+      };
+      const bool defer = p.defer && single;
+      float sv[6][4];
+      if (single) {
+        if (b_own < B) {
+          cell4(b_own, gx, sv);
+          if (!defer) store4(b_own, sv);
+        }
+      } else {
+        for (int b = b_own; b < B; b += 32) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) ld4(p.gates + (((size_t)t * B + b) * D + d) * GH + (size_t)g * H + u0 + uq, gx[g]);
+          cell4(b, gx, sv);
+          store4(b, sv);
+        }
+      }
+      if (e == 0) trace_stamp(p.trace, p.T, step, 8);
+      named_bar_sync(1, 128);          // CTA-scope: every epilogue thread's stores happen-before thread 0's release
+      if (e == 0) {
+        trace_stamp(p.trace, p.T, step, 9);
+        fence_proxy_async_global();
+        trace_stamp(p.trace, p.T, step, 10);
+        red_release(ctr, 1u);
+        trace_stamp(p.trace, p.T, step, 11);
+        trace_stamp_ns(p.trace, p.T, step, 12);
+      }
+      if (defer) {
+        if (b_own < B) store4(b_own, sv);
+        if (e == 0) trace_stamp(p.trace, p.T, step, 13);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                     // nobody exits while the peer may still write into its tile
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+static size_t fwd_splitk_smem_bytes(int NB, int H) {
+  using namespace rp;
+  size_t NBp = NB + 1, PS = ((NB + 3) & ~3) + 4;
+  return 1024 + (size_t)(H / 128) * (128 * 128 + (size_t)NB * 128) + (128 * PS + UT * NBp + NB + 4) * sizeof(float) +
+         12 * sizeof(uint64_t) + 64;
+}
+
+// returns 1 when the shape / device does not take this variant (the caller then uses the 16-unit resident kernel)
+template <int RNN>
+static int launch_fwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
+  using namespace rp;
+  constexpr int G = RNN == DS2_RNN_LSTM ? 4 : 3;
+  if (a.H % 128 != 0 || a.H / 128 > 32) return 1;
+  if (!vec_ok(a.gates, a.hseq, a.aux) || !a.aux) return 1;
+  if (ws_bytes < res_ws_bytes(G, a.T, a.B, a.H, a.D)) return 1;
+  PersistParams p{};
+  p.T = a.T; p.B = a.B; p.NB = (a.B + 15) / 16 * 16;   // MMA M = 128 needs N % 16 == 0
+  p.H = a.H; p.D = a.D; p.NT = a.H / 32; p.G = G;
+  p.training = a.training;
+  p.len = a.len; p.gates = a.gates; p.hseq = a.hseq; p.aux = a.aux;
+  p.trace = trace_ptr_from_env("DS2_TRACE_FWD");
+  p.defer = sweep_defer_default();
+  set_acc_layout(p);
+  p.err = static_cast<int*>(ws);
+  p.bar = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + 128);
+  __half* w16 = reinterpret_cast<__half*>(static_cast<char*>(ws) + 4096);
+  p.h16 = reinterpret_cast<__half*>(static_cast<char*>(ws) + 4096 + align_up((size_t)a.D * G * a.H * a.H * 2, 256));
+  const size_t smem = one_cta_per_sm(fwd_splitk_smem_bytes(p.NB, a.H));
+  if (smem > 227 * 1024) return 1;
+  auto kern = rnn_fwd_splitk_kernel<RNN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  int grid = a.D * p.NT * 2, launches = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = 2; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeCooperative;
+  attrs[1].val.cooperative = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = getenv("DS2_SPLITK_NONCOOP") ? 1 : 2;     // see the backward launcher (Nsight Compute)
+  int max_clusters = 0;
+  cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+  if (oe != cudaSuccess) { (void)cudaGetLastError(); return 1; }
+  if (max_clusters * 2 < grid) {
+    if (max_clusters * 2 < p.NT * 2) return 1;
+    grid = p.NT * 2;
+    launches = a.D;
+    cfg.gridDim = dim3(grid);
+  }
+  const size_t wn = (size_t)G * a.H * a.H;
+  for (int d = 0; d < a.D; ++d) {
+    p.b_ih[d] = a.b_ih[d];
+    p.b_hh[d] = a.b_hh[d];
+    DS2_LAUNCH(f32_to_f16_kernel, 148 * 4, 256, 0, st, wn, a.w_hh[d], w16 + (size_t)d * wn);
+    int rc = make_tmap_f16(&p.tmW[d], w16 + (size_t)d * wn, 3, a.H, a.H, G, (size_t)a.H, (size_t)a.H * a.H, 64, UT, G);
+    if (rc) return rc;
+    rc = make_tmap_f16(&p.tmV[d], p.h16 + (size_t)d * a.T * a.B * a.H, 2, a.H, a.T * a.B, 1, (size_t)a.H, 0, 64, a.B, 1);
+    if (rc) return rc;
+    p.box3 = (a.H / 128) % 4 == 0;
+    if (p.box3) {
+      rc = make_tmap_f16(&p.tmV3[d], p.h16 + (size_t)d * a.T * a.B * a.H, 3, 64, a.T * a.B, a.H / 64, (size_t)a.H, 64, 64,
+                         p.NB, 4);
+      if (rc) return rc;
+    }
+  }
+  DS2_CHECK_CUDA(cudaMemsetAsync(ws, 0, 4096, st));
+  for (int li = 0; li < launches; ++li) {
+    p.d0 = li;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
+    if (le != cudaSuccess) {
+      (void)cudaGetLastError();
+      if (li == 0) return 1;
+      set_error("split-K forward sweep: second launch failed: %s", cudaGetErrorString(le));
+      return DS2_ERR_CUDA;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  return DS2_OK;
+}
+
 static size_t splitk_smem_bytes(int NB, int CL) {
   using namespace rp;
   size_t NBp = NB + 1;
@@ -1479,6 +1875,7 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
   const int GH = G * a.H;
   constexpr int UM = UT * CL;
   if (a.H % UM != 0 || GH % CL != 0 || (GH / CL) % 64 != 0 || (GH / CL) / 64 > 120) return 1;   // <= 32 group barriers
+  if (CL == 8 && ((a.B + 7) / 8 * 8) % 16 != 0) return 1;                                       // M = 128: N % 16 == 0
   if (!vec_ok(a.gates, a.hseq, a.aux, a.dy)) return 1;
   if (ws_bytes < splitk_res_ws_bytes(G, a.T, a.B, a.H, a.D)) return 1;
   PersistParams p{};
@@ -1574,6 +1971,7 @@ static int launch_bwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
   }
   constexpr int UM = UT * CL;
   if (a.H % UM != 0 || (GH / CL) % BK != 0 || GH % CL != 0) return 1;
+  if (CL == 8 && ((a.B + 7) / 8 * 8) % 16 != 0) return 1;
   if (!vec_ok(a.gates, a.hseq, a.aux, a.dy)) return 1;
   PersistParams p{};
   p.T = a.T; p.B = a.B; p.NB = (a.B + 7) / 8 * 8; p.H = a.H; p.D = a.D; p.NT = a.H / UM; p.G = G;
