@@ -954,6 +954,16 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     }
   }
 }
+// Layout of the partial tiles exchanged inside a cluster: [source CTA][group of 4 columns][row position][4 columns].
+// A lane owns an accumulator row, so for one group of 4 columns the 32 lanes of a warp store to (nearly)
+// consecutive 16-byte slots (with a [row][column] layout every lane hit a different 144-byte row: ~170 cycles
+// per st.async instruction).  Rows are skewed by one slot every 8 rows so that the reader's rows r, r+4, r+8,
+// r+12 fall into different banks, and a column group is padded by one slot.
+__host__ __device__ constexpr int xt_cgs(int rows) { return (rows + rows / 8) * 4 + 4; }                   // floats / group
+__host__ __device__ constexpr int xt_slice(int rows, int nb) { return (nb / 4) * xt_cgs(rows); }           // floats / source
+__device__ __forceinline__ int xt_off(int rows, int row, int col) {
+  return (col >> 2) * xt_cgs(rows) + (row + (row >> 3)) * 4 + (col & 3);
+}
 // 16-byte store into a cluster peer's shared memory that also counts 16 bytes on the peer's mbarrier
 // (st.async: data and completion travel together, no fence / separate arrive on the critical path)
 __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, float a, float b, float c, float d, uint32_t cluster_bar) {
@@ -1000,9 +1010,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
   const int NKR = (G * H / CL) / 64;                                     // resident: 64 fp16 of K per chunk
   const int NG = grp_count(NKR);
   const int ring_bytes = RES ? NKR * STAGE_BYTES : STAGES * STAGE_BYTES;
-  const int PS = ((NB + 3) & ~3) + 4;                                    // row pitch of the received tiles (16 B aligned)
-  float* part = reinterpret_cast<float*>(smem + ring_bytes);             // [CL sources][16][PS] partial dh_rec
-  float* cst = part + UM * PS;                                           // [16][NBp] carried dc / dh
+  float* part = reinterpret_cast<float*>(smem + ring_bytes);             // [CL sources] partial dh_rec tiles (xt_* layout)
+  float* cst = part + CL * xt_slice(UT, NB);                             // [16][NBp] carried dc / dh
   int* lens_s = reinterpret_cast<int*>(cst + UT * NBp);
   unsigned int* cta_max = reinterpret_cast<unsigned int*>(lens_s + ((NB + 1) & ~1));   // [2] (8 bytes)
   uint64_t* full = reinterpret_cast<uint64_t*>(cta_max + 2);             // resident: one per group of 4 chunks
@@ -1172,7 +1181,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
     // split with lane+16 by shuffle.  M = 128 (CL 8): lane l of quarter q holds row 32q+l -> CTA 2q + l/16, all 32
     // columns of the row are sent by that lane.
     const int dst_cta = CL == 4 ? q : 2 * q + half;
-    const uint32_t dst_row = mapa_u32(smem_u32(part), (uint32_t)dst_cta) + (uint32_t)((ks * UT + ul) * PS * 4);
+    const uint32_t dst_row = mapa_u32(smem_u32(part), (uint32_t)dst_cta) + (uint32_t)(ks * xt_slice(UT, NB) * 4);
     const uint32_t dst_bar = mapa_u32(smem_u32(part_bar), (uint32_t)dst_cta);
     const uint32_t part_tx = (uint32_t)(CL * UT * NB * 4);               // bytes this CTA receives per step
     // resident: s_cur scales what this step writes, s_prev un-scales what this step's MMAs consumed
@@ -1283,13 +1292,15 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int c0 = cb + half * 16 + 4 * i;      // NB is a multiple of 8: a group of 4 columns is in or out
-              if (c0 < NB) st_async_v4(dst_row + (uint32_t)(c0 * 4), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], dst_bar);
+              if (c0 < NB)
+                st_async_v4(dst_row + (uint32_t)(xt_off(UT, ul, c0) * 4), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], dst_bar);
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int c0 = cb + 4 * i;
-              if (c0 < NB) st_async_v4(dst_row + (uint32_t)(c0 * 4), acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3], dst_bar);
+              if (c0 < NB)
+                st_async_v4(dst_row + (uint32_t)(xt_off(UT, ul, c0) * 4), acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3], dst_bar);
             }
           }
         }
@@ -1330,9 +1341,10 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
         for (int j = 0; j < NPF; ++j) {
           float rec = 0.f;
           if (step > 0) {
-            const float* pr = part + (uq + j) * PS + b;
-            rec = (pr[0] + pr[UT * PS]) + (pr[2 * UT * PS] + pr[3 * UT * PS]);
-            if (CL == 8) rec += (pr[4 * UT * PS] + pr[5 * UT * PS]) + (pr[6 * UT * PS] + pr[7 * UT * PS]);
+            const float* pr = part + xt_off(UT, uq + j, b);
+            const int ss = xt_slice(UT, NB);
+            rec = (pr[0] + pr[ss]) + (pr[2 * ss] + pr[3 * ss]);
+            if (CL == 8) rec += (pr[4 * ss] + pr[5 * ss]) + (pr[6 * ss] + pr[7 * ss]);
           }
           dh[j] = dyv[j] + (RES ? rec * inv_prev : rec);
         }
@@ -1466,11 +1478,10 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __
   const int NB = p.NB, B = p.B, T = p.T, H = p.H, D = p.D;
   const int B_BYTES = NB * 128;
   const int NBp = NB + 1;
-  const int PS = ((NB + 3) & ~3) + 4;                    // row pitch of the received tiles (16 B aligned)
   const int NKR = H / 128;                               // 64-wide fp16 chunks of this CTA's K half
   const int NG = grp_count(NKR);
-  float* part = reinterpret_cast<float*>(smem + NKR * (AW + B_BYTES));   // [2 sources][64 rows][PS]
-  float* cst = part + 128 * PS;                                          // [16][NBp] cell (LSTM) / hidden (GRU) state
+  float* part = reinterpret_cast<float*>(smem + NKR * (AW + B_BYTES));   // [2 sources] 64-row partial tiles (xt_* layout)
+  float* cst = part + 2 * xt_slice(64, NB);                              // [16][NBp] cell (LSTM) / hidden (GRU) state
   int* lens_s = reinterpret_cast<int*>(cst + UT * NBp);
   uint64_t* full = reinterpret_cast<uint64_t*>(lens_s + ((NB + 1) & ~1));   // one per group of 4 chunks (<= 8)
   uint64_t* wbar = full + 8;
@@ -1572,8 +1583,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __
     const int e = threadIdx.x - 64;          // 0..127
     // TMEM lane (= row) 32q + lane belongs to CTA q/2; inside that CTA's 64-row slice it is row 32 (q&1) + lane
     const int dst_cta = q >> 1;
-    const uint32_t dst_row = mapa_u32(smem_u32(part), (uint32_t)dst_cta) +
-                             (uint32_t)((rank * 64 + 32 * (q & 1) + lane) * PS * 4);
+    const int my_row = 32 * (q & 1) + lane;
+    const uint32_t dst_row = mapa_u32(smem_u32(part), (uint32_t)dst_cta) + (uint32_t)(rank * xt_slice(64, NB) * 4);
     const uint32_t dst_bar = mapa_u32(smem_u32(part_bar), (uint32_t)dst_cta);
     const uint32_t part_tx = (uint32_t)(2 * 64 * NB * 4);
     const int uq = 4 * (e & 3), b_own = e >> 2;
@@ -1615,7 +1626,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int c0 = cb + 4 * i;                    // NB is a multiple of 8: a group of 4 columns is in or out
-            if (c0 < NB) st_async_v4(dst_row + (uint32_t)(c0 * 4), acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3], dst_bar);
+            if (c0 < NB)
+              st_async_v4(dst_row + (uint32_t)(xt_off(64, my_row, c0) * 4), acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3], dst_bar);
           }
         }
         acc_phase ^= 1;
@@ -1635,8 +1647,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __
           for (int j = 0; j < 4; ++j) {
             float r = 0.f;
             if (step > 0) {
-              const float* pr = part + (g * UT + uq + j) * PS + b;
-              r = pr[0] + pr[64 * PS];
+              const float* pr = part + xt_off(64, g * UT + uq + j, b);
+              r = pr[0] + pr[xt_slice(64, NB)];
             }
             if (RNN == DS2_RNN_GRU && g == 2) { hn[j] = r + bhn[j]; pre[g][j] = x[g][j] + bsum[g][j]; }
             else pre[g][j] = (x[g][j] + r) + bsum[g][j];
@@ -1750,8 +1762,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __
 
 static size_t fwd_splitk_smem_bytes(int NB, int H) {
   using namespace rp;
-  size_t NBp = NB + 1, PS = ((NB + 3) & ~3) + 4;
-  return 1024 + (size_t)(H / 128) * (128 * 128 + (size_t)NB * 128) + (128 * PS + UT * NBp + NB + 4) * sizeof(float) +
+  size_t NBp = NB + 1;
+  return 1024 + (size_t)(H / 128) * (128 * 128 + (size_t)NB * 128) + (2 * xt_slice(64, NB) + UT * NBp + NB + 4) * sizeof(float) +
          12 * sizeof(uint64_t) + 64;
 }
 
@@ -1839,9 +1851,8 @@ static int launch_fwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
 static size_t splitk_smem_bytes(int NB, int CL) {
   using namespace rp;
   size_t NBp = NB + 1;
-  size_t PS = ((NB + 3) & ~3) + 4;
   return 1024 + (size_t)STAGES * ((size_t)UT * CL * 128 + (size_t)NB * 128) +
-         ((size_t)UT * CL * PS + UT * NBp + NB + 8) * sizeof(float) + (2 * STAGES + 3) * sizeof(uint64_t) + 64;
+         ((size_t)CL * xt_slice(UT, NB) + UT * NBp + NB + 8) * sizeof(float) + (2 * STAGES + 3) * sizeof(uint64_t) + 64;
 }
 
 // max |x| over n floats -> atomicMax on float bits (x >= 0 after fabs)
@@ -1857,9 +1868,8 @@ __global__ void absmax_kernel(size_t n, const float* __restrict__ x, unsigned in
 static size_t splitk_res_smem_bytes(int NB, int Kc, int CL) {
   using namespace rp;
   size_t NBp = NB + 1;
-  size_t PS = ((NB + 3) & ~3) + 4;
   return 1024 + (size_t)(Kc / 64) * ((size_t)UT * CL * 128 + (size_t)NB * 128) +
-         ((size_t)UT * CL * PS + UT * NBp + NB + 8) * sizeof(float) + (32 + STAGES + 3) * sizeof(uint64_t) + 64;
+         ((size_t)CL * xt_slice(UT, NB) + UT * NBp + NB + 8) * sizeof(float) + (32 + STAGES + 3) * sizeof(uint64_t) + 64;
 }
 // workspace of the resident backward: [4 KB control][gmax D*(T+1) uints][W^T fp16: D*H*GH][dg16: T*B*D*GH]
 static size_t splitk_res_ws_bytes(int G, int T, int B, int H, int D) {
