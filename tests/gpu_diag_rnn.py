@@ -1,4 +1,5 @@
-"""Not a test: recurrent-layer bring-up diagnostics. fp32 FFMA step kernels vs tcgen05 persistent sweep."""
+"""Not a test: recurrent-layer bring-up diagnostics. fp32 FFMA step kernels vs tcgen05 persistent sweep.
+(In-kernel clock64 traces: tests/gpu_diag_sweep.py.)"""
 import ctypes
 import os
 import sys
@@ -82,28 +83,6 @@ def timing(rnn, bidir, T, B, In, H, bn, iters=3):
         print(f"timing {prec} {rnn} bidir={bidir} T={T} B={B} In={In} H={H}: {out}", flush=True)
 
 
-def trace(rnn, bidir, T, B, In, H, bn):
-    """per-step clock64 stamps of CTA 0 inside the persistent sweeps"""
-    x, lens, ws, bnp = make(rnn, bidir, T, B, In, H, bn, ragged=False)
-    dy = torch.randn(T, B, H)
-    run("tf32", rnn, bidir, x, lens, ws, bnp, dy)
-    tf = torch.zeros(6 * T, dtype=torch.int64, device="cuda")
-    tb = torch.zeros(6 * T, dtype=torch.int64, device="cuda")
-    os.environ["DS2_TRACE_FWD"] = str(tf.data_ptr())
-    os.environ["DS2_TRACE_BWD"] = str(tb.data_ptr())
-    run("tf32", rnn, bidir, x, lens, ws, bnp, dy)
-    del os.environ["DS2_TRACE_FWD"], os.environ["DS2_TRACE_BWD"]
-    for name, tr in (("fwd", tf), ("bwd", tb)):
-        a = tr.cpu().view(T, 6).double()
-        names = ["barrier", "first_full", "last_full", "accum_done", "exchange", "arrive"]
-        print(f"trace {name}: SM cycles relative to the previous step's arrive (median over steps 10..T-10)")
-        prev = a[9:T - 11, 5].unsqueeze(1)
-        relc = (a[10:T - 10] - prev)
-        med = relc.median(0).values
-        print("   " + "  ".join(f"{n}={int(m)}" for n, m in zip(names, med.tolist())), flush=True)
-        print("   step period (cycles): median", int((a[11:T - 10, 5] - a[10:T - 11, 5]).median()), flush=True)
-
-
 def main():
     print(torch.cuda.get_device_name(0))
     for args in [("lstm", True, 20, 5, 64, 64, False), ("lstm", True, 37, 32, 96, 128, True), ("gru", True, 25, 7, 64, 64, True),
@@ -112,10 +91,6 @@ def main():
             compare(*args)
         except Exception:
             print("[EXC]", args, traceback.format_exc(), flush=True)
-    try:
-        trace("lstm", True, 200, 32, 1024, 1024, True)
-    except Exception:
-        print("[EXC] trace", traceback.format_exc(), flush=True)
     try:
         timing("lstm", True, 500, 32, 1024, 1024, True)
     except Exception:
