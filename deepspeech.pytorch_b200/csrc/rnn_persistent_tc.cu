@@ -522,6 +522,15 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
   }
 }
 
+// A sweep whose barrier wait timed out (or that found an unexpected TMEM base) leaves garbage behind: fail loudly.
+// Runs right after every sweep launch; the trap makes the next CUDA call of the process return an error.
+__global__ void sweep_check_kernel(const int* err) {
+  if (*err != 0) {
+    printf("ds2: recurrent sweep failed (code %d): results are invalid\n", *err);
+    __trap();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Every persistent CTA allocates all 512 TMEM columns, so two of them must never share an SM (the second
 // tcgen05.alloc would block while the first waits for it at the grid barrier): ask for more than half of
@@ -654,6 +663,7 @@ static int launch_fwd_resident(const SeqArgs& a, void* ws, size_t ws_bytes, cuda
     DS2_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(THREADS), args, smem, st));
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
+  DS2_LAUNCH(sweep_check_kernel, 1, 1, 0, st, p.err);
   return DS2_OK;
 }
 
@@ -716,6 +726,7 @@ static int launch_fwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t 
     DS2_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(THREADS), args, smem, st));
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
+  DS2_LAUNCH(sweep_check_kernel, 1, 1, 0, st, p.err);
   return DS2_OK;
 }
 
@@ -1845,6 +1856,7 @@ static int launch_fwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
+  DS2_LAUNCH(sweep_check_kernel, 1, 1, 0, st, p.err);
   return DS2_OK;
 }
 
@@ -1966,6 +1978,7 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
+  DS2_LAUNCH(sweep_check_kernel, 1, 1, 0, st, p.err);
   if (a.dbias_done && a.dbias[0]) *a.dbias_done = 1;
   return DS2_OK;
 }
@@ -2046,6 +2059,7 @@ static int launch_bwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
+  DS2_LAUNCH(sweep_check_kernel, 1, 1, 0, st, p.err);
   return DS2_OK;
 }
 
@@ -2103,6 +2117,7 @@ static int launch_bwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t 
     DS2_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(THREADS), args, smem, st));
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
+  DS2_LAUNCH(sweep_check_kernel, 1, 1, 0, st, p.err);
   return DS2_OK;
 }
 
