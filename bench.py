@@ -246,10 +246,14 @@ def run_b200(args):
     x_dev = x.to(dev)
     targets_pinned = targets.pin_memory()
 
+    # one all-reduce of the flat gradient buffer, its (99.7 %) recurrent + fc part started as soon as those
+    # gradients are final so that it overlaps the conv backward
+    exchange = D.OverlappedGradAllReduce(flat, model)
+
     def train_step(inputs):
         loss = model.training_step((inputs, targets_pinned, pct.clone(), tsz), 0)
         loss.backward()
-        D.allreduce_flat_grad(flat.grad)
+        exchange.finish()
         opt.step(grad_scale=1.0 / world)
         flat.zero_grad()
         return loss

@@ -42,6 +42,45 @@ def allreduce_flat_grad(flat_grad: torch.Tensor, async_op: bool = False):
     return dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, async_op=async_op)
 
 
+class OverlappedGradAllReduce:
+    """The same single-buffer exchange, split in two so that most of it hides behind the conv backward.
+
+    Parameters are laid out in `model.parameters()` order: the conv front-end first (0.3 % of the buffer), then
+    the recurrent stack and the fc head.  The front-end's backward runs LAST, and by the time autograd reaches it
+    every gradient of the tail [split:] is final (AccumulateGrad nodes run before the next function node).
+    `DeepSpeech.front_end_grad_hook` fires exactly there: the tail's all-reduce is started asynchronously (NCCL
+    orders it after the work already queued on the compute stream) and overlaps the ~5 ms conv backward;
+    `finish()` after `backward()` reduces the small head and waits for the tail."""
+
+    def __init__(self, flat, model):
+        self.flat = flat
+        conv_ids = {id(p) for p in model.conv.parameters()}
+        split = 0
+        for p, o in zip(flat.params, flat.offsets):
+            if id(p) in conv_ids:
+                split = max(split, o + (p.numel() + 63) // 64 * 64)
+        # the conv parameters must form a prefix of the buffer, otherwise fall back to one exchange in finish()
+        prefix_ok = all((id(p) in conv_ids) == (o < split) for p, o in zip(flat.params, flat.offsets))
+        self.split = split if prefix_ok else flat.n
+        self.work = None
+        model.front_end_grad_hook = self._tail_ready
+
+    def _tail_ready(self):
+        if world_size() > 1 and self.split < self.flat.n:
+            self.work = dist.all_reduce(self.flat.grad[self.split:], op=dist.ReduceOp.SUM, async_op=True)
+
+    def finish(self):
+        if world_size() == 1:
+            return
+        if self.split > 0:
+            dist.all_reduce(self.flat.grad[:self.split], op=dist.ReduceOp.SUM)
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        elif self.split < self.flat.n:       # hook did not fire (e.g. frozen front-end): exchange the tail now
+            dist.all_reduce(self.flat.grad[self.split:], op=dist.ReduceOp.SUM)
+
+
 def broadcast_buffers(model, src: int = 0):
     if world_size() == 1:
         return

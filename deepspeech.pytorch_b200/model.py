@@ -140,6 +140,11 @@ class DeepSpeech(_Base):
         if training:
             sm[1].num_batches_tracked += 1
             sm[4].num_batches_tracked += 1
+            hook = getattr(self, "front_end_grad_hook", None)
+            if hook is not None and y.requires_grad:
+                # fires when autograd reaches the front-end, i.e. when every other gradient is final
+                # (dist.OverlappedGradAllReduce starts the exchange of those gradients here)
+                y.register_hook(lambda g, _h=hook: _h())
         t_out = min(int(max(ol)), y.shape[0])
         y = y[:t_out]                                                           # pad_packed_sequence truncation
         if hs is None:

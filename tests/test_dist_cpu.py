@@ -38,6 +38,24 @@ def _worker(rank, world, port, out):
     D.broadcast_buffers(m, src=0)
     assert float(m.running_mean[0]) == 1.0
     assert D.shard_bins(7, rank, world) == list(range(7))[rank::world]
+    # split exchange (conv head / recurrent+fc tail) == one all-reduce of the whole buffer
+    from deepspeech_pytorch_b200.optim import FlatParams
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Linear(5, 7)
+            self.rest = torch.nn.Linear(7, 3)
+    tiny = Tiny()
+    flat = FlatParams(tiny)
+    ex = D.OverlappedGradAllReduce(flat, tiny)
+    assert 0 < ex.split < flat.n
+    for fire_hook in (True, False):
+        flat.grad.copy_(torch.arange(flat.n, dtype=torch.float32) * (rank + 1))
+        if fire_hook:
+            tiny.front_end_grad_hook()          # what DeepSpeech.forward's tensor hook does during backward
+        ex.finish()
+        assert torch.allclose(flat.grad, torch.arange(flat.n, dtype=torch.float32) * sum(range(1, world + 1)))
     dist.destroy_process_group()
     out.put(rank)
 
