@@ -441,7 +441,7 @@ int gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const floa
     if (forced >= 1 && forced <= 3) {
       cfg = (forced == 2 && M < 256) ? 1 : forced;
     } else if (M >= 256) {
-      if (tiles2 >= 120) cfg = 2;
+      if (tiles2 >= 90) cfg = 2;      // (96 tiles: the 4096 x 1312 first-layer weight gradient, one wave)
       else if (tiles2 * 2 >= 100 && tiles2 * 2 <= 148 && K >= 2048 && (beta == 0.f || beta == 1.f)) { cfg = 2; splits = 2; }
     }
   }

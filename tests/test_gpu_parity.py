@@ -305,3 +305,84 @@ def test_tf32_stress_shape_h1536_one_launch_per_direction():
     assert rel(a[0], b_[0]) < 5e-3 and rel(a[1], b_[1]) < 5e-3 and rel_l2(a[2], b_[2]) < 1e-2
     for ga, gb in zip(a[3], b_[3]):
         assert rel_l2(ga, gb) < 1e-2
+
+
+# ---- kernel variants behind the tensor-core mode: every selectable path must give the same answer ----------
+def _one_layer(rnn, T, B, In, H, seed):
+    from deepspeech_pytorch_b200 import _lib
+    G = {"lstm": 4, "gru": 3}[rnn]
+    code = {"lstm": _lib.RNN_LSTM, "gru": _lib.RNN_GRU}[rnn]
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(T, B, In, generator=g).cuda()
+    lens = torch.tensor(sorted([max(1, T - 2 * i) for i in range(B)], reverse=True), dtype=torch.int32)
+    for b in range(B):
+        x[int(lens[b]):, b] = 0
+    k = 1.0 / H ** 0.5
+    ws = [((torch.rand(s, generator=g) * 2 - 1) * k).cuda().requires_grad_(True) for s in
+          [(G * H, In), (G * H, H), (G * H,), (G * H,)] * 2]
+    dy = torch.randn(T, B, H, generator=g).cuda()
+    for b in range(B):
+        dy[int(lens[b]):, b] = 0
+
+    def run():
+        for w in ws:
+            w.grad = None
+        xx = x.clone().requires_grad_(True)
+        y, hn, cn = ds.ops.RnnLayer.apply(xx, lens.cuda(), code, True, True, 0.1, 1e-5, None, None, None, None, None,
+                                          None, *ws)
+        y.backward(dy)
+        torch.cuda.synchronize()
+        return [y.detach(), hn.detach(), xx.grad.clone()] + [w.grad.clone() for w in ws]
+    return run
+
+
+@pytest.mark.parametrize("rnn,B", [("lstm", 32), ("lstm", 20), ("gru", 20)])
+def test_tf32_sweep_variants_agree_with_the_fp32_path(rnn, B, monkeypatch):
+    """forward: 2-CTA split-K clusters vs 16-unit CTAs; backward: 8- vs 4-CTA clusters (LSTM, B = 32); stores deferred
+    past the barrier arrival or not.  H = 256 takes every variant; B = 20 exercises the N padding (24 / 32 columns)."""
+    run = _one_layer(rnn, T=33, B=B, In=192, H=256, seed=11)
+    ds.set_precision("fp32")
+    ref = run()
+    ds.set_precision("tf32")
+    variants = [{}, {"DS2_FWD_SPLITK": "0"}, {"DS2_SPLITK_CL": "4"}, {"DS2_SWEEP_DEFER": "0"},
+                {"DS2_FWD_SPLITK": "0", "DS2_SPLITK_CL": "4", "DS2_SWEEP_DEFER": "0"}]
+    for env in variants:
+        for k_, v in env.items():
+            monkeypatch.setenv(k_, v)
+        got = run()
+        for k_ in env:
+            monkeypatch.delenv(k_)
+        assert rel(got[0], ref[0]) < 5e-3 and rel(got[1], ref[1]) < 5e-3, env
+        for a, b in zip(got[2:], ref[2:]):
+            assert rel_l2(a, b) < 1e-2, env
+
+
+@pytest.mark.parametrize("cfg", ["1", "2", "3"])
+def test_gemm_tile_configurations_vs_fp64(cfg, monkeypatch):
+    """128x256x4 stages, 256x256x3 stages (two TMEM accumulators), 128x256x2 stages with two CTAs per SM; K-major and
+    MN-major operands (3-D boxes when the extent is a multiple of 32, 2-D boxes otherwise); TF32 error level."""
+    monkeypatch.setenv("DS2_GEMM_CFG", cfg)
+    ds.set_precision("tf32")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for tA, tB, M, N, K in [(0, 1, 600, 520, 300), (1, 0, 512, 320, 2000), (0, 0, 640, 1312, 512),
+                            (1, 1, 424, 96, 100), (1, 0, 500, 260, 1000)]:
+        a = torch.randn((K, M) if tA else (M, K), generator=g, device="cuda")
+        b = torch.randn((N, K) if tB else (K, N), generator=g, device="cuda")
+        ref = (a.t() if tA else a).double() @ (b.t() if tB else b).double()
+        c = ds.ops.gemm(a, b, bool(tA), bool(tB))
+        assert rel_l2(c, ref) < 1e-3, (cfg, tA, tB, M, N, K)
+
+
+def test_gemm_split_k_accumulates_into_c():
+    """weight-gradient shape class (64 tiles of 256x256): 2-way split-K with vector atomics, beta = 0 and beta = 1"""
+    ds.set_precision("tf32")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 4096, 1024, 2304
+    a = torch.randn(K, M, generator=g, device="cuda")
+    b = torch.randn(K, N, generator=g, device="cuda")
+    ref = a.t().double() @ b.double()
+    c = ds.ops.gemm(a, b, True, False)
+    assert rel_l2(c, ref) < 1e-3
+    c0 = torch.randn(M, N, generator=g, device="cuda")
+    c1 = ds.ops.gemm(a, b, True, False, out=c0.clone(), alpha=0.5, beta=1.0)
+    assert rel_l2(c1, 0.5 * ref + c0.double()) < 1e-3
