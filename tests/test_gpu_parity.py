@@ -336,10 +336,11 @@ def _one_layer(rnn, T, B, In, H, seed):
     return run
 
 
-@pytest.mark.parametrize("rnn,B", [("lstm", 32), ("lstm", 20), ("gru", 20)])
+@pytest.mark.parametrize("rnn,B", [("lstm", 32), ("lstm", 20), ("gru", 20), ("lstm", 40), ("gru", 48)])
 def test_tf32_sweep_variants_agree_with_the_fp32_path(rnn, B, monkeypatch):
     """forward: 2-CTA split-K clusters vs 16-unit CTAs; backward: 8- vs 4-CTA clusters (LSTM, B = 32); stores deferred
-    past the barrier arrival or not.  H = 256 takes every variant; B = 20 exercises the N padding (24 / 32 columns)."""
+    past the barrier arrival or not.  H = 256 takes every variant; B = 20 exercises the N padding (24 / 32 columns),
+    B > 32 the second pass of the epilogues over the batch columns."""
     run = _one_layer(rnn, T=33, B=B, In=192, H=256, seed=11)
     ds.set_precision("fp32")
     ref = run()
