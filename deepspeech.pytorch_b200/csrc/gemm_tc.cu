@@ -332,6 +332,164 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_dealloc<G::TMEM_COLS>(tmem_base);
 }
 
+// ---- EXPERIMENTAL, not selected automatically (DS2_GEMM_CFG=4), NOT yet run on hardware ------------------
+// 256 x 256 tiles in 2-CTA clusters along M that SHARE the B tile: each CTA loads its own A tile (32 KB per K
+// chunk) and one half of the B tile (16 KB), multicast into both CTAs' shared memory.  Per CTA that is 48 KB of
+// L2 reads per 1024 tensor-pipe cycles = 47 B/cycle/SM, just above what the L2 delivers to all SMs at once
+// (the 256 x 256 single-CTA tile needs 64, the 128 x 256 tile 94).  A stage may be refilled only when BOTH CTAs'
+// MMAs have read it (the peer's multicast writes into it too): the `empty` barriers count two arrivals, and every
+// tcgen05.commit is multicast to the pair.
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(tc::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                               int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(tc::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   tc::smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_gemm() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(gtc::THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                    float alpha, float beta, float* __restrict__ C, int ldc, unsigned int mn_cfg, int mn3d) {
+  using namespace gtc;
+  using namespace tc;
+  using G = Cfg<2, 3>;
+  constexpr int BM = G::BM, STAGES = G::STAGES, STAGE_BYTES = G::STAGE_BYTES, A_BYTES = G::A_BYTES;
+  constexpr int BH = G::B_BYTES / 2;                      // half of the B tile: 128 rows / 4 MN blocks
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum_bar = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int rank = (int)cluster_rank();                   // cluster = two consecutive blockIdx.y
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nk = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<G::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_gemm();                                    // the peer's barriers exist before anything is multicast
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);                     // both CTAs have released slot s
+        mbar_arrive_expect_tx(&full[s], STAGE_BYTES);     // own A + both halves of B
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        if (A_MN) tma_load_3d(sa, &tmA, &full[s], 0, it * BK, m0 / 32);
+        else tma_load_2d(sa, &tmA, &full[s], it * BK, m0);
+        uint8_t* sb = sa + A_BYTES + rank * BH;           // this CTA's half, same offset in both CTAs
+        if (B_MN) tma_load_3d_mc(sb, &tmB, &full[s], 0, it * BK, n0 / 32 + rank * 4, (uint16_t)3);
+        else tma_load_2d_mc(sb, &tmB, &full[s], it * BK, n0 + rank * 128, (uint16_t)3);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc(FMT_TF32, 128, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+      const uint32_t mn_layout = mn_cfg & 7u, lbo = ((mn_cfg >> 4) & 0x3FFFu) << 4, sbo = (mn_cfg >> 18) << 4;
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES), b_addr = smem_u32(smem + s * STAGE_BYTES + A_BYTES);
+        const uint64_t adesc = A_MN ? smem_desc_mn(a_addr, mn_layout, lbo, sbo) : smem_desc_sw128(a_addr);
+        const uint64_t bdesc = B_MN ? smem_desc_mn(b_addr, mn_layout, lbo, sbo) : smem_desc_sw128(b_addr);
+        constexpr uint64_t a_adv = A_MN ? 64 : 2, b_adv = B_MN ? 64 : 2;
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k)
+            mma_tf32(tmem_base + (uint32_t)(mb * 256), adesc + (uint64_t)(mb * 1024) + (uint64_t)k * a_adv,
+                     bdesc + (uint64_t)k * b_adv, idesc, (it | k) != 0);
+        }
+        mma_commit_mc(&empty[s], (uint16_t)3);            // slot s of THIS CTA is free: tell both producers
+      }
+      mma_commit(accum_bar);
+    }
+  } else if (nk > 0) {
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int q = warp % 4;
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll 1
+    for (int mb = 0; mb < 2; ++mb) {
+      const int row = m0 + mb * 128 + q * 32 + lane;
+      if (m0 + mb * 128 >= M) break;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= N) break;
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * 256 + c * 32), v);
+        if (row < M) {
+          float* cp = C + (size_t)row * ldc + col0;
+          if (vec_ok && col0 + 32 <= N) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 o = make_float4(alpha * v[4 * j], alpha * v[4 * j + 1], alpha * v[4 * j + 2], alpha * v[4 * j + 3]);
+              if (beta != 0.f) {
+                float4 old = *reinterpret_cast<const float4*>(cp + 4 * j);
+                o.x = fmaf(beta, old.x, o.x); o.y = fmaf(beta, old.y, o.y);
+                o.z = fmaf(beta, old.z, o.z); o.w = fmaf(beta, old.w, o.w);
+              }
+              *reinterpret_cast<float4*>(cp + 4 * j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) {
+                float o = alpha * v[j];
+                if (beta != 0.f) o = fmaf(beta, cp[j], o);
+                cp[j] = o;
+              }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_gemm();                                    // the peer may still multicast / arrive until it is done too
+  if (warp == 1) tmem_dealloc<G::TMEM_COLS>(tmem_base);
+}
+
 // out (C x R, pitch ldo) = in (R x C, pitch ldi)^T
 __global__ void transpose_strided_kernel(int R, int C, const float* __restrict__ in, size_t ldi,
                                          float* __restrict__ out, size_t ldo) {
@@ -396,6 +554,33 @@ static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M,
   return DS2_OK;
 }
 
+template <bool A_MN, bool B_MN>
+static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, float alpha, float beta,
+                            float* C, int ldc, int mn3d, cudaStream_t st) {
+  using G = gtc::Cfg<2, 3>;
+  auto kern = gemm_tc_pair_kernel<A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+    attr_set = true;
+  }
+  const MnCfg mc = mn_cfg_from_env();
+  const unsigned int mn_cfg = (unsigned)(mc.layout & 7) | ((unsigned)(mc.lbo >> 4) << 4) | ((unsigned)(mc.sbo >> 4) << 18);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cdiv(N, gtc::BN), (cdiv(M, G::BM) + 1) / 2 * 2);    // whole pairs; surplus rows are masked
+  cfg.blockDim = dim3(gtc::THREADS);
+  cfg.dynamicSmemBytes = G::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 1; attr.val.clusterDim.y = 2; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  DS2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, M, N, K, alpha, beta, C, ldc, mn_cfg, mn3d));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return DS2_OK;
+}
+
 int gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
             int ldb, float beta, float* C, int ldc, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (!tc_eligible(M, N, K)) return 1;
@@ -438,14 +623,17 @@ int gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const floa
     const char* e = getenv("DS2_GEMM_CFG");
     const int forced = e ? atoi(e) : 0;
     const long long tiles2 = (long long)cdiv(M, 256) * cdiv(N, gtc::BN);
-    if (forced >= 1 && forced <= 3) {
+    if (forced >= 1 && forced <= 4) {
       cfg = (forced == 2 && M < 256) ? 1 : forced;
+      // 4 (experimental CTA-pair kernel): MN-major operands only through 3-D boxes, no split-K
+      if (cfg == 4 && (M < 256 || (a_mn && M % 32 != 0) || (b_mn && N % 32 != 0))) cfg = 1;
     } else if (M >= 256) {
       if (tiles2 >= 90) cfg = 2;      // (96 tiles: the 4096 x 1312 first-layer weight gradient, one wave)
       else if (tiles2 * 2 >= 100 && tiles2 * 2 <= 148 && K >= 2048 && (beta == 0.f || beta == 1.f)) { cfg = 2; splits = 2; }
     }
   }
-  const int bm = cfg == 2 ? 256 : 128;
+  const int bm = (cfg == 2 || cfg == 4) ? 256 : 128;
+  const int bn_box = cfg == 4 ? gtc::BN / 2 : gtc::BN;      // pair kernel: each CTA loads half of the B tile
   CUtensorMap tmA, tmB;
   // K-major: matrix [rows, K] box (32 k, rows).  MN-major: matrix [K, rows]: one 3-D box (32 rows, 32 k, blocks)
   // when rows % 32 == 0, else 2-D boxes (32 rows, 32 k)
@@ -460,11 +648,17 @@ int gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const floa
   if (rc) return rc;
   if (b_mn && N % 32 == 0) {
     mn3d |= 2;
-    rc = make_tmap_3d_sw(&tmB, Bk, 32, K, N / 32, (size_t)ldbk, 32, 32, 32, gtc::BN / 32, mn_sw);
+    rc = make_tmap_3d_sw(&tmB, Bk, 32, K, N / 32, (size_t)ldbk, 32, 32, 32, bn_box / 32, mn_sw);
   } else {
-    rc = b_mn ? make_tmap_2d_sw(&tmB, Bk, K, N, ldbk, 32, 32, mn_sw) : make_tmap_2d(&tmB, Bk, N, K, ldbk, gtc::BN, gtc::BK);
+    rc = b_mn ? make_tmap_2d_sw(&tmB, Bk, K, N, ldbk, 32, 32, mn_sw) : make_tmap_2d(&tmB, Bk, N, K, ldbk, bn_box, gtc::BK);
   }
   if (rc) return rc;
+  if (cfg == 4) {
+    if (a_mn && b_mn) return launch_gemm_pair<true, true>(tmA, tmB, M, N, K, alpha, beta, C, ldc, mn3d, st);
+    if (a_mn) return launch_gemm_pair<true, false>(tmA, tmB, M, N, K, alpha, beta, C, ldc, mn3d, st);
+    if (b_mn) return launch_gemm_pair<false, true>(tmA, tmB, M, N, K, alpha, beta, C, ldc, mn3d, st);
+    return launch_gemm_pair<false, false>(tmA, tmB, M, N, K, alpha, beta, C, ldc, mn3d, st);
+  }
 #define DS2_GEMM_DISPATCH(AM, BMN)                                                                                   \
   return cfg == 2   ? launch_gemm_tc<AM, BMN, 2, 3>(tmA, tmB, M, N, K, alpha, beta, C, ldc, mn3d, splits, st)        \
          : cfg == 3 ? launch_gemm_tc<AM, BMN, 1, 2>(tmA, tmB, M, N, K, alpha, beta, C, ldc, mn3d, splits, st)        \

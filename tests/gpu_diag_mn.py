@@ -57,6 +57,22 @@ def main():
         timing(0, 1, 16000, 4096, 1024)    # projection
         timing(0, 1, 16000, 8192, 1312)
     del os.environ["DS2_GEMM_CFG"]
+    # experimental CTA-pair kernel (B tile multicast inside 2-CTA clusters): LAST, it has never run on hardware;
+    # run this script under `timeout` the first time
+    if os.environ.get("DS2_DIAG_PAIR"):
+        os.environ["DS2_GEMM_CFG"] = "4"
+        print("=== DS2_GEMM_CFG 4 (256x256 tiles, 2-CTA clusters sharing the B tile)", flush=True)
+        for args in [(0, 1, 512, 512, 256), (0, 1, 600, 520, 300), (1, 0, 512, 320, 2000), (0, 0, 640, 1312, 512),
+                     (1, 1, 4096, 1024, 4100)]:
+            try:
+                one(*args)
+            except Exception:
+                print("[EXC]", args, traceback.format_exc(), flush=True)
+        timing(1, 0, 4096, 1024, 16000)
+        timing(0, 0, 16000, 1024, 4096)
+        timing(0, 1, 16000, 4096, 1024)
+        timing(0, 1, 16000, 8192, 1312)
+        del os.environ["DS2_GEMM_CFG"]
 
 
 if __name__ == "__main__":
