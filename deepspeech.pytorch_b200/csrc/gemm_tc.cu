@@ -332,7 +332,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_dealloc<G::TMEM_COLS>(tmem_base);
 }
 
-// ---- EXPERIMENTAL, not selected automatically (DS2_GEMM_CFG=4), NOT yet run on hardware ------------------
+// ---- Not selected automatically (DS2_GEMM_CFG=4): correct on hardware (bit-identical results,
+// profiles/r01_gemm_pair_kernel.txt) but no faster than the single-CTA 256 x 256 tile — the limit is the
+// shared-memory bandwidth of each SM (TMA fill + MMA operand reads), not the L2 reads this variant halves.
+// Kept as the cluster / multicast plumbing for a cta_group::2 version.
 // 256 x 256 tiles in 2-CTA clusters along M that SHARE the B tile: each CTA loads its own A tile (32 KB per K
 // chunk) and one half of the B tile (16 KB), multicast into both CTAs' shared memory.  Per CTA that is 48 KB of
 // L2 reads per 1024 tensor-pipe cycles = 47 B/cycle/SM, just above what the L2 delivers to all SMs at once

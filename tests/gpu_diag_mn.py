@@ -29,7 +29,27 @@ def timing(tA, tB, M, N, K, iters=10):
           flush=True)
 
 
+def pair_kernel():
+    """CTA-pair kernel (B tile multicast inside 2-CTA clusters), DS2_GEMM_CFG=4"""
+    os.environ["DS2_GEMM_MN_MAJOR"] = "1"
+    os.environ["DS2_GEMM_CFG"] = "4"
+    print("=== DS2_GEMM_CFG 4 (256x256 tiles, 2-CTA clusters sharing the B tile)", flush=True)
+    for args in [(0, 1, 512, 512, 256), (0, 1, 600, 520, 300), (1, 0, 512, 320, 2000), (0, 0, 640, 1312, 512),
+                 (1, 1, 4096, 1024, 4100)]:
+        try:
+            one(*args)
+        except Exception:
+            print("[EXC]", args, traceback.format_exc(), flush=True)
+    timing(1, 0, 4096, 1024, 16000)
+    timing(0, 0, 16000, 1024, 4096)
+    timing(0, 1, 16000, 4096, 1024)
+    timing(0, 1, 16000, 8192, 1312)
+    del os.environ["DS2_GEMM_CFG"]
+
+
 def main():
+    if os.environ.get("DS2_DIAG_PAIR") == "only":
+        return pair_kernel()
     # tma_swizzle (3 = 128B, 4 = 128B_ATOM_32B), descriptor layout type, LBO, SBO
     for cfg in ("4,1,4096,512",):
         os.environ["DS2_GEMM_MN_MAJOR"] = "1"
@@ -57,23 +77,8 @@ def main():
         timing(0, 1, 16000, 4096, 1024)    # projection
         timing(0, 1, 16000, 8192, 1312)
     del os.environ["DS2_GEMM_CFG"]
-    # experimental CTA-pair kernel (B tile multicast inside 2-CTA clusters): LAST, it has never run on hardware;
-    # run this script under `timeout` the first time
     if os.environ.get("DS2_DIAG_PAIR"):
-        os.environ["DS2_GEMM_CFG"] = "4"
-        print("=== DS2_GEMM_CFG 4 (256x256 tiles, 2-CTA clusters sharing the B tile)", flush=True)
-        for args in [(0, 1, 512, 512, 256), (0, 1, 600, 520, 300), (1, 0, 512, 320, 2000), (0, 0, 640, 1312, 512),
-                     (1, 1, 4096, 1024, 4100)]:
-            try:
-                one(*args)
-            except Exception:
-                print("[EXC]", args, traceback.format_exc(), flush=True)
-        timing(1, 0, 4096, 1024, 16000)
-        timing(0, 0, 16000, 1024, 4096)
-        timing(0, 1, 16000, 4096, 1024)
-        timing(0, 1, 16000, 8192, 1312)
-        del os.environ["DS2_GEMM_CFG"]
-
+        pair_kernel()
 
 if __name__ == "__main__":
     main()
