@@ -36,6 +36,19 @@ WORKLOADS = {
 T0 = time.time()
 
 
+def synth_batch(B, T, L, seed):
+    """SURVEY.md §8d throughput inputs: N(0,1) spectrograms (B,1,161,T), every utterance T frames long
+    (percentages 1.0), every target L labels drawn from 1..28 (0 is the CTC blank); flat int64 targets and int32
+    target sizes exactly as the reference's _collate_fn emits them (data_loader.py:247-270)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 1, 161, T, generator=g)
+    pct = torch.ones(B, dtype=torch.float32)
+    tsz = torch.full((B,), L, dtype=torch.int32)
+    targets = torch.randint(1, 29, (B * L,), generator=g, dtype=torch.int64)
+    return x, targets, pct, tsz
+
+
 def log(msg):
     if int(os.environ.get("RANK", "0")) == 0:
         print(f"[bench +{time.time() - T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
@@ -171,46 +184,171 @@ def cpu_baseline(workload, timeout_s=150):
         return {"value": None, "unit": "utt/s", "cores": host_cores(), "kind": "port", "sample": f"failed: {e!r}"}
 
 
-def stock_cuda_baseline(workload, steps=5, warmup=2):
-    """north_star's denominator: the reference's stock PyTorch CUDA path (cuDNN conv/RNN with TF32 allowed,
-    ATen CTC, torch AdamW) — same ATen calls as reference model.py, issued by the oracle port on the GPU."""
-    import torch
+def _oracle_cfg(workload):
     from oracle import ds2_oracle as O
     rnn, bidir, H, layers, ctx, B, T, L = WORKLOADS[workload]
-    dev = torch.device("cuda", torch.cuda.current_device())
-    ocfg = O.OracleConfig(rnn_type=rnn, hidden_size=H, hidden_layers=layers, bidirectional=bidir,
+    return O.OracleConfig(rnn_type=rnn, hidden_size=H, hidden_layers=layers, bidirectional=bidir,
                           lookahead_context=ctx)
-    P = {k: v.to(dev) for k, v in O.init_params(ocfg, seed=123456).items()}
-    leaves = {k: v.clone().requires_grad_(True) for k, v in P.items() if v.dtype.is_floating_point and "running_" not in k}
-    opt = torch.optim.AdamW(list(leaves.values()), lr=1.5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
-    x, targets, pct, tsz = O.synth_batch(B, T, seed=1234, ragged=False, lmin=L, lmax=L)
-    x = x.to(dev)
+
+
+def stock_cuda_baseline(workload, P0, batch, steps=5, warmup=3):
+    """north_star's denominator: the reference's stock PyTorch CUDA path — the ATen calls of reference model.py
+    (cuDNN conv / packed cuDNN RNN, ATen CTC, clip_grad_norm_, torch AdamW) issued by the oracle port on the GPU,
+    starting from the SAME weights and the SAME batch as the B200 arm.  Three variants so that the comparison is
+    not against a handicapped baseline:
+      default      torch's default flags (cudnn.allow_tf32=True, matmul.allow_tf32=False, cudnn.benchmark=False —
+                   reference lightning_config.py:59), fp32
+      cudnn_bench  same with cudnn.benchmark=True
+      amp_fp16     torch.autocast(float16) + GradScaler: the reference's shipped `precision: 16`
+                   (configs/librispeech.yaml:12)"""
+    import torch
     import torch.nn.functional as F
+    from oracle import ds2_oracle as O
+    rnn, bidir, H, layers, ctx, B, T, L = WORKLOADS[workload]
+    ocfg = _oracle_cfg(workload)
+    x, targets, pct, tsz = batch
+    dev = x.device
+    res = {}
+    saved = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    for name, bench_flag, amp in (("default", False, False), ("cudnn_bench", True, False), ("amp_fp16", False, True)):
+        try:
+            torch.backends.cudnn.benchmark = bench_flag
+            torch.backends.cudnn.allow_tf32 = True
+            torch.backends.cuda.matmul.allow_tf32 = False
+            P = {k: v.detach().clone() for k, v in P0.items()}
+            leaves = {k: v.requires_grad_(True) for k, v in P.items()
+                      if v.dtype.is_floating_point and "running_" not in k}
+            opt = torch.optim.AdamW(list(leaves.values()), lr=1.5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
+            scaler = torch.amp.GradScaler("cuda", enabled=amp)
+            sizes = O.input_sizes_from_percentages(pct.clone(), T)
 
-    def step():
-        Q = dict(P)
-        Q.update(leaves)
-        sizes = O.input_sizes_from_percentages(pct, T)
-        out, osz, _, _ = O.forward(x, sizes, Q, ocfg, training=True, use_aten_rnn=True)
-        loss = F.ctc_loss(out.transpose(0, 1).log_softmax(-1), targets, osz, tsz, blank=0, reduction="sum",
+            def step():
+                with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+                    out, osz, _, nb = O.forward(x, sizes, P, ocfg, training=True, use_aten_rnn=True)
+                    loss = F.ctc_loss(out.transpose(0, 1).float().log_softmax(-1), targets, osz, tsz, blank=0,
+                                      reduction="sum", zero_infinity=True)
+                for k, v in nb.items():          # running statistics advance like nn.BatchNorm's buffers
+                    P[k] = v.detach()
+                opt.zero_grad(set_to_none=True)
+                scaler.scale(loss).backward()
+                scaler.unscale_(opt)
+                torch.nn.utils.clip_grad_norm_(list(leaves.values()), 400.0)
+                scaler.step(opt)
+                scaler.update()
+                return loss
+
+            first = None
+            for i in range(warmup):
+                l = step()
+                if i == 0:
+                    first = float(l.detach())
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            res[name] = {"value": B / (ms * 1e-3), "unit": "utt/s", "ms_per_step": ms, "steps": steps,
+                         "first_step_loss": first}
+        except Exception as e:  # pragma: no cover
+            res[name] = {"error": repr(e)[:300]}
+        finally:
+            (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32,
+             torch.backends.cuda.matmul.allow_tf32) = saved
+        torch.cuda.empty_cache()
+    res["kind"] = ("stock torch CUDA ops (cuDNN conv/RNN, ATen CTC, clip_grad_norm_, torch AdamW) issued by the "
+                   "oracle port; same initial weights and batch as the B200 arm")
+    return res
+
+
+def _group_of(name):
+    if name.startswith("conv."):
+        return "conv"
+    if name.startswith("rnns."):
+        i = name.split(".")[1]
+        kind = ("bn" if "batch_norm" in name else "w_ih" if "weight_ih" in name else
+                "w_hh" if "weight_hh" in name else "bias")
+        return f"rnn{i}.{kind}"
+    if name.startswith("lookahead"):
+        return "lookahead"
+    return "fc.bn" if "module.0" in name else "fc.w"
+
+
+def parity_fullsize(workload, model, flat, P0, batch):
+    """The benchmarked configuration against the fp32 reference arithmetic, at full size and with the same weights:
+    the B200 arm (current precision mode) vs the reference's own ATen calls on the GPU with every TF32 switch OFF
+    (cuDNN fp32 conv/RNN, fp32 matmul) and the CTC lattice in float64.  `oracle/` is the checker here, nothing of
+    it is timed.  Reports logits / loss / per-parameter-group gradient errors (rel = max|a-b| / max|b|,
+    rel_l2 = ||a-b|| / ||b||)."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import ds2_oracle as O
+    rnn, bidir, H, layers, ctx, B, T, L = WORKLOADS[workload]
+    ocfg = _oracle_cfg(workload)
+    x, targets, pct, tsz = batch
+    sizes = O.input_sizes_from_percentages(pct.clone(), T)
+
+    def rel(a, b):
+        d = float(b.abs().max())
+        return float((a - b).abs().max()) / (d if d > 0 else 1.0)
+
+    def rel_l2(a, b):
+        d = float(b.double().norm())
+        return float((a.double() - b.double()).norm()) / (d if d > 0 else 1.0)
+
+    # ---- reference arithmetic (fp32 everywhere, CTC in fp64)
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+    try:
+        P = {k: v.detach().clone() for k, v in P0.items()}
+        leaves = {k: v.requires_grad_(True) for k, v in P.items() if v.dtype.is_floating_point and "running_" not in k}
+        out, osz, _, _ = O.forward(x, sizes, P, ocfg, training=True, use_aten_rnn=True)
+        loss = F.ctc_loss(out.transpose(0, 1).double().log_softmax(-1), targets, osz, tsz, blank=0, reduction="sum",
                           zero_infinity=True)
-        opt.zero_grad(set_to_none=True)
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(list(leaves.values()), 400.0)
-        opt.step()
-
-    for _ in range(warmup):
-        step()
+        ref_logits, ref_loss = out.detach(), float(loss.detach())
+        ref_grads = {k: v.grad.detach() for k, v in leaves.items()}
+        del out, loss
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    # ---- B200 arm, same weights
+    model.load_state_dict(P0)
+    flat.zero_grad()
+    got_logits, _, _ = model(x, sizes)
+    got_logits = got_logits.detach().clone()
+    model.load_state_dict(P0)                       # undo the running-statistics update of that forward
+    flat.zero_grad()
+    loss = model.training_step((x, targets, pct.clone(), tsz), 0)
+    loss.backward()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    return {"value": B / (ms * 1e-3), "unit": "utt/s", "ms_per_step": ms, "kind": "stock torch CUDA ops (cuDNN TF32 "
-            "conv/RNN, ATen CTC, torch AdamW) issued by the oracle port", "steps": steps}
+    got_loss = float(loss.detach())
+    groups = {}
+    for k, p in model.named_parameters():
+        g = _group_of(k)
+        a, b = p.grad.detach().reshape(-1), ref_grads[k].reshape(-1)
+        acc = groups.setdefault(g, [0.0, 0.0, 0.0, 0.0])
+        acc[0] += float((a.double() - b.double()).pow(2).sum())
+        acc[1] += float(b.double().pow(2).sum())
+        acc[2] = max(acc[2], float((a - b).abs().max()))
+        acc[3] = max(acc[3], float(b.abs().max()))
+    res = {
+        "reference": "reference ATen ops on the GPU, cudnn.allow_tf32=False, matmul.allow_tf32=False, CTC in float64; "
+                     "same weights, same batch",
+        "logits_rel": rel(got_logits, ref_logits), "logits_rel_l2": rel_l2(got_logits, ref_logits),
+        "loss": got_loss, "loss_reference": ref_loss, "loss_rel": abs(got_loss - ref_loss) / max(1.0, abs(ref_loss)),
+        "grad_rel_l2": {g: (v[0] / v[1]) ** 0.5 if v[1] > 0 else 0.0 for g, v in sorted(groups.items())},
+        "grad_rel_max": {g: v[2] / v[3] if v[3] > 0 else 0.0 for g, v in sorted(groups.items())},
+        "finite": bool(all(torch.isfinite(p.grad).all() for p in model.parameters())),
+    }
+    model.load_state_dict(P0)
+    flat.zero_grad()
+    del ref_grads, ref_logits, got_logits
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_b200(args):
@@ -218,7 +356,6 @@ def run_b200(args):
     import deepspeech_pytorch_b200 as ds
     from deepspeech_pytorch_b200 import dist as D
     from deepspeech_pytorch_b200.optim import FlatParams, FusedOptimizer
-    from oracle import ds2_oracle as O   # synthetic batch generator + cpu_baseline leg only
 
     # NCCL prints its version banner on stdout: keep fd 1 clean for the single JSON line
     saved_stdout = os.dup(1)
@@ -241,7 +378,9 @@ def run_b200(args):
     opt = FusedOptimizer(flat, model.optim_cfg, max_norm=400.0)
     n_params = sum(p.numel() for p in model.parameters())
 
-    x, targets, pct, tsz = O.synth_batch(B, T, seed=1234 + rank, ragged=False, lmin=L, lmax=L)
+    # the weights every arm of this run starts from (B200 timing, full-size parity check, stock CUDA baseline)
+    P0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    x, targets, pct, tsz = synth_batch(B, T, L, seed=1234 + rank)
     x_pinned = x.pin_memory()
     x_dev = x.to(dev)
     targets_pinned = targets.pin_memory()
@@ -285,6 +424,18 @@ def run_b200(args):
             ms = float(t)
         return ms / n, launches, (last if e2e else float(last.detach()))
 
+    parity = None
+    if world == 1 and not args.no_parity:
+        log("full-size parity check against the fp32 reference arithmetic (same weights, same batch)")
+        try:
+            parity = parity_fullsize(args.workload, model, flat, P0, (x_dev, targets, pct, tsz))
+            log("parity_fullsize: " + json.dumps(parity))
+        except Exception as e:  # pragma: no cover
+            parity = {"error": repr(e)[:300]}
+            log(f"parity_fullsize failed: {e!r}")
+        model.load_state_dict(P0)
+        flat.zero_grad()
+    lib.ds2_fallback_count(1)
     log(f"model built ({n_params} params), warming up")
     for _ in range(max(3, args.warmup)):
         train_step(x_dev)
@@ -345,6 +496,18 @@ def run_b200(args):
                           "ms_per_launch": ms_launch, "ms_per_step": prof[tag]["ms_per_step"],
                           "note": "latency-bound: T' serial steps of (grid barrier + MMA issue chain + epilogue); "
                                   "see DESIGN.md 5.1"}
+    if "ctc" in prof and prof["ctc"]["ms_per_step"] > 0:
+        # read logits (T'*B*C*4) + write grad (same) + targets / lengths; the alpha/beta tables the
+        # kernel keeps (or spills) are overhead, not credit
+        Cn = 29
+        ctc_bytes = 2 * Tp * B * Cn * 4 + B * L * 8 + 2 * B * 4
+        ach = ctc_bytes / (prof["ctc"]["ms_per_step"] * 1e-3) / 1e9
+        roofs["ctc"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                        "traffic": traffic_db.get("ctc", {}).get("dram_bytes_per_launch"), "peak_source": which,
+                        "algorithmic_bytes_per_launch": ctc_bytes, "launches_per_step": 1,
+                        "ms_per_launch": prof["ctc"]["ms_per_step"], "ms_per_step": prof["ctc"]["ms_per_step"],
+                        "note": "latency-bound: T' dependent lattice steps per utterance, B*2 CTAs; the HBM fraction "
+                                "is not the binding limit (DESIGN.md 5.4)"}
     dominant = max(prof, key=lambda k: prof[k]["ms_per_step"]) if prof else None
     roofline = roofs.get(dominant) or (roofs.get("rnn_bwd_sweep") if roofs else None)
     if roofline is not None:
@@ -357,25 +520,38 @@ def run_b200(args):
         "metric": "utterances/sec (train step, 161x1000 spectrogram)", "value": value, "unit": "utt/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_dev,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+        "dtype": "tf32+fp16-recurrent" if args.precision == "tf32" else "f32", "data": "synthetic",
+        "dtype_note": ("dense GEMMs / conv2: TF32 operands (TMA rounds to nearest); recurrent products: fp16 operands "
+                       "(10-bit mantissa like TF32; backward gate gradients scaled per step by a power of two); fp32 "
+                       "accumulation in TMEM, fp32 state / activations / gradients / optimizer"
+                       if args.precision == "tf32" else "fp32 FFMA everywhere"),
         "config": {"workload": args.workload, "rnn": f"{layers}x{'bi' if bidir else 'uni'}-{rnn}-{H}",
                    "batch_per_gpu": B, "global_batch": B * world, "frames": T, "target_len": L, "params": n_params,
                    "parallelism": f"dp{world}", "optimizer": "fused clip(400)+AdamW inside the step",
                    "l2": "per-step working set (activations 3+ GB) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e, "unit": "utt/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
-        "gpu_launches": launches, "clocks": clocks, "loss": loss_val,
+        "gpu_launches": launches, "ffma_fallback_sweeps": int(lib.ds2_fallback_count(0)), "clocks": clocks,
+        "loss": loss_val, "parity_fullsize": parity,
         "roofline": roofline, "roofline_all": roofs, "blocks_ms_per_step": {k: v["ms_per_step"] for k, v in prof.items()},
     }
     log("profile ranges: " + json.dumps(line["blocks_ms_per_step"]))
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.workload)
         log("cpu baseline done")
-    if args.stock_cuda:
+    if world == 1 and not args.no_stock_cuda:
+        log("stock torch CUDA baseline (north_star denominator), same weights")
         try:
-            line["stock_cuda_baseline"] = stock_cuda_baseline(args.workload)
+            torch.cuda.empty_cache()
+            sc = stock_cuda_baseline(args.workload, P0, (x_dev, targets, pct, tsz))
+            line["stock_cuda_baseline"] = sc
+            line["vs_stock_cuda"] = {k: (value / v["value"]) for k, v in sc.items()
+                                     if isinstance(v, dict) and v.get("value")}
+            line["vs_stock_cuda_e2e"] = {k: (e2e / v["value"]) for k, v in sc.items()
+                                         if isinstance(v, dict) and v.get("value")}
         except Exception as e:  # pragma: no cover
-            line["stock_cuda_baseline"] = {"error": repr(e)}
+            line["stock_cuda_baseline"] = {"error": repr(e)[:300]}
+        log("stock baseline done: " + json.dumps(line.get("vs_stock_cuda")))
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
@@ -395,7 +571,9 @@ def main():
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=2, help="--impl reference: utterances per CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--stock-cuda", action="store_true", help="also time the stock torch CUDA path (north_star denominator)")
+    ap.add_argument("--stock-cuda", action="store_true", help="(default on at N=1; kept for compatibility)")
+    ap.add_argument("--no-stock-cuda", action="store_true", help="skip the stock torch CUDA baseline legs")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-size parity check against fp32 ATen")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

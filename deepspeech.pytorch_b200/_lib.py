@@ -27,6 +27,7 @@ PROTOTYPES = {
     "ds2_set_precision": (i32, [i32]),
     "ds2_get_precision": (i32, []),
     "ds2_launch_count": (i64, [i32]),
+    "ds2_fallback_count": (i64, [i32]),
     "ds2_prof_enable": (i32, [i32]),
     "ds2_prof_report": (i32, [C.c_char_p, sz]),
     "ds2_seq_lens_host": (i32, [vp, i32, vp]),

@@ -21,6 +21,30 @@ void set_error(const char* fmt, ...) {
 }
 int precision() { return g_prec.load(std::memory_order_relaxed); }
 
+int device_sm_count() {
+  static std::atomic<int> cache[64];
+  const int d = current_device();
+  int v = cache[d].load(std::memory_order_relaxed);
+  if (v <= 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess) { (void)cudaGetLastError(); v = 0; }
+    cache[d].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+std::atomic<long long> g_fallbacks{0};
+void note_fallback(const char* what, int rnn, int T, int B, int H, int D) {
+  static std::mutex mu;
+  static std::map<std::string, int> seen;
+  g_fallbacks.fetch_add(1, std::memory_order_relaxed);
+  char key[160];
+  snprintf(key, sizeof(key), "%s rnn=%d B=%d H=%d D=%d", what, rnn, B, H, D);
+  std::lock_guard<std::mutex> lk(mu);
+  if (seen[key]++ == 0)
+    fprintf(stderr, "ds2_b200: WARNING tensor-core mode: %s (T=%d) is not eligible for the persistent tcgen05 sweep; "
+                    "using one FFMA launch per time step (slow). ds2_fallback_count() counts these.\n", key, T);
+}
+
 // ---- profiler -----------------------------------------------------------------------------------
 struct ProfRec { const char* tag; cudaEvent_t e0, e1; };
 static std::vector<ProfRec> g_recs;
@@ -82,6 +106,11 @@ int ds2_get_precision(void) { return ds2::precision(); }
 
 int64_t ds2_launch_count(int reset) {
   long long v = reset ? ds2::g_launches.exchange(0) : ds2::g_launches.load();
+  return (int64_t)v;
+}
+
+int64_t ds2_fallback_count(int reset) {
+  long long v = reset ? ds2::g_fallbacks.exchange(0) : ds2::g_fallbacks.load();
   return (int64_t)v;
 }
 

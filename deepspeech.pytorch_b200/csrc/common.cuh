@@ -16,6 +16,24 @@ int precision();
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Host-side "once per device" latch: cudaFuncSetAttribute and the device attributes are per device, so a plain
+// function-local static would leave the second GPU of a process without its shared-memory opt-in.
+inline int current_device() {
+  int d = 0;
+  (void)cudaGetDevice(&d);
+  return d & 63;
+}
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool first() const { return !((mask.load(std::memory_order_acquire) >> current_device()) & 1ull); }
+  void done() { mask.fetch_or(1ull << current_device(), std::memory_order_release); }
+};
+int device_sm_count();   // SM count of the current device (cached per device)
+
+// A tensor-core-mode call that had to take the one-launch-per-time-step FFMA kernels (shape not eligible for the
+// persistent sweeps): counted and reported once per shape on stderr, never silent.
+void note_fallback(const char* what, int rnn, int T, int B, int H, int D);
+
 #define DS2_CHECK_CUDA(expr)                                                             \
   do {                                                                                   \
     cudaError_t _e = (expr);                                                             \

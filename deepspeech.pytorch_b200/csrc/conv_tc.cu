@@ -248,10 +248,10 @@ int conv_tc_run(const float* in_cl, int B, int T, int R_in, int R_out, const flo
   p.row_mul = row_mul; p.row_off = row_off; p.row_step = row_step; p.w_off = w_off; p.w_step = w_step;
   p.out = out; p.ob = ob; p.oc = oc; p.orow = orow; p.out_row_mul = out_row_mul; p.out_row_off = out_row_off;
   p.bias = bias; p.out_len = out_len; p.stat_sums = stat_sums;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     DS2_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cv::SMEM_BYTES));
-    attr_done = true;
+    attr_once.done();
   }
   dim3 grid(cdiv(T, cv::TO), R_out, B);
   DS2_LAUNCH(conv_tc_kernel, grid, cv::THREADS, cv::SMEM_BYTES, st, p);
@@ -455,10 +455,10 @@ int conv2_wgrad_tc(const float* dz2, const float* a1, float* a1_shifted /* 4*B*3
     if (rc) return rc;
   }
   p.B = B; p.T = T; p.slices = 7; p.dw2 = dw2;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     DS2_CHECK_CUDA(cudaFuncSetAttribute(conv2_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
-    attr_done = true;
+    attr_once.done();
   }
   DS2_LAUNCH(conv2_wgrad_tc_kernel, dim3(21, p.slices), wg::THREADS, wg::SMEM_BYTES, st, p);
   return DS2_OK;

@@ -543,10 +543,10 @@ static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M,
                           float* C, int ldc, int mn3d, int splits, cudaStream_t st) {
   using G = gtc::Cfg<NMB, STG>;
   auto kern = gemm_tc_kernel<A_MN, B_MN, NMB, STG>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-    attr_set = true;
+    attr_once.done();
   }
   const MnCfg mc = mn_cfg_from_env();
   const unsigned int mn_cfg = (unsigned)(mc.layout & 7) | ((unsigned)(mc.lbo >> 4) << 4) | ((unsigned)(mc.sbo >> 4) << 18);
@@ -562,10 +562,10 @@ static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, int 
                             float* C, int ldc, int mn3d, cudaStream_t st) {
   using G = gtc::Cfg<2, 3>;
   auto kern = gemm_tc_pair_kernel<A_MN, B_MN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-    attr_set = true;
+    attr_once.done();
   }
   const MnCfg mc = mn_cfg_from_env();
   const unsigned int mn_cfg = (unsigned)(mc.layout & 7) | ((unsigned)(mc.lbo >> 4) << 4) | ((unsigned)(mc.sbo >> 4) << 18);

@@ -339,7 +339,10 @@ int ds2_rnn_layer_fwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
   {
     DS2_PROF("rnn_fwd_sweep", st);
     rc = 1;
-    if (precision() == DS2_PREC_TF32) rc = rnn_sweep_fwd_tc(d->rnn_type, a, gws, gws_bytes, st);
+    if (precision() == DS2_PREC_TF32) {
+      rc = rnn_sweep_fwd_tc(d->rnn_type, a, gws, gws_bytes, st);
+      if (rc == 1) note_fallback("forward sweep", d->rnn_type, T, B, H, D);
+    }
     if (rc == 1) rc = sweep_fwd(d->rnn_type, a, st);
     if (rc) return rc;
   }
@@ -403,7 +406,10 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
   {
     DS2_PROF("rnn_bwd_sweep", st);
     rc = 1;
-    if (precision() == DS2_PREC_TF32) rc = rnn_sweep_bwd_tc(d->rnn_type, a, gws, gws_bytes, st);
+    if (precision() == DS2_PREC_TF32) {
+      rc = rnn_sweep_bwd_tc(d->rnn_type, a, gws, gws_bytes, st);
+      if (rc == 1) note_fallback("backward sweep", d->rnn_type, T, B, H, D);
+    }
     if (rc == 1) rc = sweep_bwd(d->rnn_type, a, st);
     if (rc) return rc;
   }

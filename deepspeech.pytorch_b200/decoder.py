@@ -26,10 +26,31 @@ class GreedyDecoder:
         offsets = torch.zeros(B, T, dtype=torch.int32, device=dev)
         counts = torch.zeros(B, dtype=torch.int32, device=dev)
         sz = None if sizes is None else torch.as_tensor(sizes).int().to(dev)
-        check(get_lib().ds2_greedy_decode(B, T, Cn, ptr(probs), ptr(sz), self.blank_index, ptr(labels), ptr(offsets),
-                                          ptr(counts), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
-              "ds2_greedy_decode")
+        with torch.cuda.device(dev):                         # launches bind to the current device
+            check(get_lib().ds2_greedy_decode(B, T, Cn, ptr(probs), ptr(sz), self.blank_index, ptr(labels),
+                                              ptr(offsets), ptr(counts),
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                  "ds2_greedy_decode")
         return labels.cpu(), offsets.cpu(), counts.cpu()
+
+    def convert_to_strings(self, sequences, sizes=None, remove_repetitions=False, return_offsets=False):
+        """label-index sequences -> [[str]] (decoder.py:125-163): blanks dropped, optional repeat collapsing; used by
+        the WER/CER accumulators for the reference transcripts (host integers, tiny)"""
+        strings, offsets = [], []
+        blank = self.int_to_char[self.blank_index]
+        for x in range(len(sequences)):
+            seq = [int(v) for v in sequences[x]]
+            n = int(sizes[x]) if sizes is not None else len(seq)
+            out, offs = [], []
+            for i in range(n):
+                ch = self.int_to_char[seq[i]]
+                if ch == blank or (remove_repetitions and i != 0 and seq[i] == seq[i - 1]):
+                    continue
+                out.append(ch)
+                offs.append(i)
+            strings.append([''.join(out)])
+            offsets.append([torch.tensor(offs, dtype=torch.int)])
+        return (strings, offsets) if return_offsets else strings
 
     def decode(self, probs, sizes=None):
         """same return shape as the reference: (strings [[str]], offsets [[IntTensor]])"""

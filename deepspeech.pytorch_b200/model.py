@@ -18,6 +18,7 @@ import torch.nn as nn
 from . import _lib, ops
 from .configs import cfg_type, is_kind
 from .decoder import GreedyDecoder
+from .metrics import CharErrorRate, WordErrorRate
 
 try:  # Lightning is optional: with it installed the shell is a LightningModule like the reference
     import pytorch_lightning as pl
@@ -108,7 +109,9 @@ class DeepSpeech(_Base):
         self.fc = nn.Sequential(_SequenceWiseParams(nn.Sequential(nn.BatchNorm1d(H),
                                                                    nn.Linear(H, num_classes, bias=False))))
         self.blank = self.labels.index('_')
-        self.evaluation_decoder = GreedyDecoder(self.labels)
+        self.evaluation_decoder = GreedyDecoder(self.labels)  # Decoder used for validation (model.py:204)
+        self.wer = WordErrorRate(decoder=self.evaluation_decoder, target_decoder=self.evaluation_decoder)
+        self.cer = CharErrorRate(decoder=self.evaluation_decoder, target_decoder=self.evaluation_decoder)
         self.criterion = self._ctc_criterion
 
     # ------------------------------------------------------------------ lengths (model.py:299-310)
@@ -196,6 +199,11 @@ class DeepSpeech(_Base):
         input_sizes = input_percentages.mul_(int(inputs.size(3))).int()
         out, output_sizes, _ = self(inputs.to(next(self.parameters()).device), input_sizes)
         decoded_output, _ = self.evaluation_decoder.decode(out, output_sizes)
+        self.wer(preds=out, preds_sizes=output_sizes, targets=targets, target_sizes=target_sizes)   # model.py:258-269
+        self.cer(preds=out, preds_sizes=output_sizes, targets=targets, target_sizes=target_sizes)
+        if pl is not None:
+            self.log('wer', self.wer.compute(), prog_bar=True, on_epoch=True)
+            self.log('cer', self.cer.compute(), prog_bar=True, on_epoch=True)
         return decoded_output
 
     # ------------------------------------------------------------------ optim (model.py:273-297)

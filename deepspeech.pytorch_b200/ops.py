@@ -7,6 +7,7 @@ One Function per block of the reference's hot path:
 All inputs must be fp32 CUDA tensors; anything else raises (no eager fallback).
 """
 import ctypes as C
+import functools
 
 import torch
 
@@ -17,7 +18,24 @@ _workspaces = {}
 
 
 def _stream():
+    """current stream of the CURRENT device — every op runs under `_on_device`, which makes the tensors' device
+    current first (kernels, TMA descriptors and the per-device shared-memory opt-ins all bind to it)"""
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _on_device(fn):
+    """run a Function.forward/backward with the device of its first CUDA tensor argument made current: the C
+    library launches on the current device, so a model on cuda:1 in a process whose current device is cuda:0
+    must not issue device-0 launches with device-1 pointers"""
+    @functools.wraps(fn)
+    def wrapped(ctx, *args):
+        dev = next((a.device for a in args if isinstance(a, torch.Tensor) and a.is_cuda), None)
+        if dev is None:
+            raise _lib.Ds2Error(f"{fn.__qualname__}: no CUDA tensor among the arguments (the B200 path has no CPU "
+                                "fallback)")
+        with torch.cuda.device(dev):
+            return fn(ctx, *args)
+    return wrapped
 
 
 def workspace(nbytes, device):
@@ -43,6 +61,7 @@ def _req(t, name):
 
 class ConvFrontend(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, x, out_len, w1, b1, g1, be1, rm1, rv1, w2, b2, g2, be2, rm2, rv2, training, momentum, eps):
         lib = get_lib()
         x = _req(x, "x")
@@ -64,11 +83,16 @@ class ConvFrontend(torch.autograd.Function):
         ctx.save_for_backward(x, out_len, params[0], params[2], params[3], params[6], params[8], params[9],
                               z1, a1, z2, stats)
         ctx.dims = (B, T)
+        ctx.eval_mode = not training
         return y
 
     @staticmethod
+    @_on_device
     def backward(ctx, dy):
         lib = get_lib()
+        if ctx.eval_mode:
+            raise _lib.Ds2Error("ConvFrontend.backward: forward ran with training=False; the BatchNorm backward "
+                                "implements the batch-statistics formula only")
         x, out_len, w1, g1, be1, w2, g2, be2, z1, a1, z2, stats = ctx.saved_tensors
         B, T = ctx.dims
         dy = _req(dy, "dy")
@@ -90,6 +114,7 @@ class RnnLayer(torch.autograd.Function):
     h0, c0, then per direction (w_ih, w_hh, b_ih, b_hh)."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, x, len_dev, rnn_type, bidirectional, training, momentum, eps, bn_g, bn_b, bn_rm, bn_rv, h0, c0,
                 *weights):
         lib = get_lib()
@@ -115,6 +140,13 @@ class RnnLayer(torch.autograd.Function):
                                     ptr(ws), ws.numel(), _stream()), "ds2_rnn_layer_fwd")
         ctx.desc = desc
         ctx.has_bn = bn_g is not None
+        # the C backward assumes zero initial state and batch-statistics BatchNorm, and it turns the saved gate
+        # activations into gate gradients in place: anything else must fail loudly instead of returning garbage
+        ctx.no_backward = ("forward ran with training=False (no saved gate activations, running-statistics "
+                           "BatchNorm)" if not training else
+                           "forward was given an initial state h0/c0 (the backward sweep assumes a zero initial "
+                           "state)" if (h0 is not None or c0 is not None) else None)
+        ctx.consumed = False
         ctx.save_for_backward(x, len_dev, bn_g, bn_b, reserve, *weights)
         ctx.mark_non_differentiable(hn)
         if cn is not None:
@@ -123,8 +155,15 @@ class RnnLayer(torch.autograd.Function):
         return y, hn, None
 
     @staticmethod
+    @_on_device
     def backward(ctx, dy, _dhn, _dcn):
         lib = get_lib()
+        if ctx.no_backward:
+            raise _lib.Ds2Error("RnnLayer.backward is not available: " + ctx.no_backward)
+        if ctx.consumed:
+            raise _lib.Ds2Error("RnnLayer.backward ran twice on the same graph: the saved gate activations were "
+                                "overwritten by the gate gradients of the first pass (retain_graph is not supported)")
+        ctx.consumed = True
         x, len_dev, bn_g, bn_b, reserve = ctx.saved_tensors[:5]
         weights = ctx.saved_tensors[5:]
         desc = ctx.desc
@@ -147,6 +186,7 @@ class RnnLayer(torch.autograd.Function):
 
 class Lookahead(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, x, w):
         lib = get_lib()
         x, w = _req(x, "x"), _req(w, "w")
@@ -158,6 +198,7 @@ class Lookahead(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_on_device
     def backward(ctx, dy):
         lib = get_lib()
         x, w = ctx.saved_tensors
@@ -171,6 +212,7 @@ class Lookahead(torch.autograd.Function):
 
 class FcHead(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, x, g, b, rm, rv, w, training, momentum, eps, softmax):
         lib = get_lib()
         x, g, b, rm, rv, w = (_req(t, "fc") for t in (x, g, b, rm, rv, w))
@@ -187,11 +229,16 @@ class FcHead(torch.autograd.Function):
                                   ptr(ws), ws.numel(), _stream()), "ds2_fc_head_fwd")
         ctx.save_for_backward(g, b, w, xhat, stats)
         ctx.dims = (rows, H, Cn, T, B)
+        ctx.eval_mode = not training
         return logits
 
     @staticmethod
+    @_on_device
     def backward(ctx, dlogits):
         lib = get_lib()
+        if ctx.eval_mode:
+            raise _lib.Ds2Error("FcHead.backward: forward ran with training=False; the BatchNorm backward implements "
+                                "the batch-statistics formula only")
         g, b, w, xhat, stats = ctx.saved_tensors
         rows, H, Cn, T, B = ctx.dims
         dlogits = _req(dlogits, "dlogits")
@@ -208,6 +255,7 @@ class CtcLoss(torch.autograd.Function):
     """sum over the batch of per-utterance CTC NLL (zero_infinity); logits (T,B,C) un-normalised."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, logits, targets, in_len, tgt_len, max_tgt_len, blank):
         lib = get_lib()
         logits = _req(logits, "logits")
@@ -224,6 +272,7 @@ class CtcLoss(torch.autograd.Function):
         return nll.sum()
 
     @staticmethod
+    @_on_device
     def backward(ctx, dloss):
         (grad,) = ctx.saved_tensors
         return grad * dloss, None, None, None, None, None
@@ -233,6 +282,11 @@ def gemm(a, b, trans_a=False, trans_b=False, out=None, alpha=1.0, beta=0.0):
     """C = alpha * op(a) @ op(b) + beta * C through ds2_gemm (tests / roofline bench)."""
     lib = get_lib()
     a, b = _req(a, "a"), _req(b, "b")
+    with torch.cuda.device(a.device):
+        return _gemm(lib, a, b, trans_a, trans_b, out, alpha, beta)
+
+
+def _gemm(lib, a, b, trans_a, trans_b, out, alpha, beta):
     M, K = (a.shape[1], a.shape[0]) if trans_a else a.shape
     N = b.shape[0] if trans_b else b.shape[1]
     if out is None:

@@ -53,6 +53,10 @@ class FusedOptimizer:
         self.ws = torch.zeros(64, device=dev)
 
     def step(self, grad_scale: float = 1.0):
+        with torch.cuda.device(self.flat.data.device):     # launches bind to the current device
+            self._step(grad_scale)
+
+    def _step(self, grad_scale):
         lib = get_lib()
         f = self.flat
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)

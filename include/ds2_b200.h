@@ -57,6 +57,10 @@ int ds2_set_precision(int prec);
 int ds2_get_precision(void);
 /* Kernel-launch counter (all kernels launched by this library since the last reset). */
 int64_t ds2_launch_count(int reset);
+/* Number of tensor-core-mode recurrent sweeps that had to take the one-launch-per-time-step FFMA kernels
+ * because their shape is not eligible for the persistent tcgen05 kernels (also reported once per shape on
+ * stderr): a benchmark line with a non-zero count did not run the path it claims.                      */
+int64_t ds2_fallback_count(int reset);
 
 /* Device-time ranges around the kernel groups of each block (cudaEvent pairs on the launching stream).
  * ds2_prof_report synchronises, writes "tag:total_ms:count;..." into buf and clears the records.     */

@@ -76,15 +76,31 @@ def test_state_dict_surface_matches_reference(name):
     model.load_state_dict(g.params)  # strict
 
 
-def test_default_init_is_rng_identical_to_torch_containers():
+@pytest.mark.parametrize("name", golden_names())
+def test_default_init_is_bit_identical_to_the_reference(name):
+    """The fixtures hold the state_dict the REFERENCE's own constructor produced under torch.manual_seed(123456)
+    (oracle/make_golden.py; only the BatchNorm affine parameters / running statistics were overwritten afterwards).
+    The shell keeps its parameters in the same torch container classes, created in the same order, so the same seed
+    must give bit-identical conv / recurrent / lookahead / fc weights: a drop-in replacement starts training from
+    the same point as the reference."""
+    g = Golden(name)
+    m = g.meta
+    rt = getattr(ds.RNNType, m["rnn_type"])
+    if m["bidirectional"]:
+        cfg = ds.BiDirectionalConfig(rnn_type=rt, hidden_size=m["hidden_size"], hidden_layers=m["hidden_layers"])
+    else:
+        cfg = ds.UniDirectionalConfig(rnn_type=rt, hidden_size=m["hidden_size"], hidden_layers=m["hidden_layers"],
+                                      lookahead_context=m["lookahead_context"])
     torch.manual_seed(123456)
-    a = ds.DeepSpeech(ds.LABELS, ds.BiDirectionalConfig(hidden_size=8, hidden_layers=2), 32, ds.AdamConfig(),
-                      ds.SpectConfig())
-    torch.manual_seed(123456)
-    b = ds.DeepSpeech(ds.LABELS, ds.BiDirectionalConfig(hidden_size=8, hidden_layers=2), 32, ds.AdamConfig(),
-                      ds.SpectConfig())
-    for (k, v), (_, w) in zip(a.state_dict().items(), b.state_dict().items()):
-        assert torch.equal(v, w), k
+    model = ds.DeepSpeech(ds.LABELS, cfg, 32, ds.AdamConfig(), ds.SpectConfig())
+    checked = 0
+    for k, v in model.state_dict().items():
+        is_bn = ("batch_norm" in k or "seq_module.1." in k or "seq_module.4." in k or "module.0." in k)
+        if is_bn:
+            continue
+        assert torch.equal(v, g.params[k]), k
+        checked += 1
+    assert checked >= 4 + 4 * m["hidden_layers"]
 
 
 def test_configs_mirror_reference_defaults():

@@ -45,7 +45,10 @@ def test_golden_train_step_loss_and_every_gradient(name):
     model = model_from_golden(g).train()
     pct = g.input_percentages.clone()
     loss = model.training_step((g.x.cuda(), g.targets, pct, g.target_sizes), 0)
-    assert torch.equal(pct, g.input_sizes.float()) or True           # mutated in place like model.py:243
+    # model.py:243 mutates the caller's tensor in place: afterwards it holds percentage * T (fp32), and its
+    # truncation is the reference's input_sizes (bit-exact, including the frames the fp32 product loses)
+    assert torch.equal(pct, g.input_percentages.clone().mul_(int(g.x.size(3))))
+    assert torch.equal(pct.int(), g.input_sizes)
     loss.backward()
     assert abs(float(loss) - g.loss) <= 1e-4 * max(1.0, abs(g.loss))
     grads = {k: p.grad for k, p in model.named_parameters()}
