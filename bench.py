@@ -313,6 +313,12 @@ def parity_fullsize(workload, model, flat, P0, batch):
         ref_logits, ref_loss = out.detach(), float(loss.detach())
         ref_grads = {k: v.grad.detach() for k, v in leaves.items()}
         del out, loss
+        # yardstick: the reference's own default CUDA path (cuDNN TF32 allowed) against the same fp32 arithmetic
+        torch.backends.cudnn.allow_tf32 = True
+        with torch.no_grad():
+            stock_logits, _, _, _ = O.forward(x, sizes, P0, ocfg, training=True, use_aten_rnn=True)
+        stock_rel, stock_rel_l2 = rel(stock_logits, ref_logits), rel_l2(stock_logits, ref_logits)
+        del stock_logits
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
     # ---- B200 arm, same weights
@@ -339,6 +345,7 @@ def parity_fullsize(workload, model, flat, P0, batch):
         "reference": "reference ATen ops on the GPU, cudnn.allow_tf32=False, matmul.allow_tf32=False, CTC in float64; "
                      "same weights, same batch",
         "logits_rel": rel(got_logits, ref_logits), "logits_rel_l2": rel_l2(got_logits, ref_logits),
+        "stock_default_tf32_logits_rel": stock_rel, "stock_default_tf32_logits_rel_l2": stock_rel_l2,
         "loss": got_loss, "loss_reference": ref_loss, "loss_rel": abs(got_loss - ref_loss) / max(1.0, abs(ref_loss)),
         "grad_rel_l2": {g: (v[0] / v[1]) ** 0.5 if v[1] > 0 else 0.0 for g, v in sorted(groups.items())},
         "grad_rel_max": {g: v[2] / v[3] if v[3] > 0 else 0.0 for g, v in sorted(groups.items())},
@@ -374,7 +381,7 @@ def run_b200(args):
             ds.UniDirectionalConfig(rnn_type=rt, hidden_size=H, hidden_layers=layers, lookahead_context=ctx))
     torch.manual_seed(123456)
     model = ds.DeepSpeech(ds.LABELS, mcfg, 32, ds.AdamConfig(), ds.SpectConfig()).to(dev).train()
-    flat = FlatParams(model)
+    flat = FlatParams(model, direct_grads=True)   # backward kernels write straight into the flat gradient buffer
     opt = FusedOptimizer(flat, model.optim_cfg, max_norm=400.0)
     n_params = sum(p.numel() for p in model.parameters())
 

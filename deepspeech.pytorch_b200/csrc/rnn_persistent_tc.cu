@@ -52,6 +52,8 @@ struct PersistParams {
   __half* h16;          // resident fwd: fp16 copy of hseq (D,T,B,H), the MMA operand of the next step
   __half* dg16;         // resident bwd: scaled fp16 copy of dGh (T*B, D*G*H)
   unsigned int* gmax;   // resident bwd: [D][T+1] float bits of max|dGh| per processed step (slot 0: bound from dY)
+  unsigned int* dymax;  // resident bwd: [T] float bits of max_b,u |dY[t]| (the scale of a step also covers its own dY)
+  unsigned int* gmeta;  // LL bwd: [D][T][NT*CL*4] float bits of max|dGh| per (step, epilogue warp), 0xFFFFFFFF = not yet
   long long* trace;     // optional: clock64 stamps of CTA 0, 4 per step
   const int32_t* len;
   float* gates;
@@ -169,6 +171,68 @@ __device__ __forceinline__ int grp_count(int nkr) { return (nkr + 3) / 4; }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+// ---- flag-in-data exchange ("LL": the data is its own ready flag) ---------------------------------------------
+// The per-step grid barrier costs store -> MEMBAR.ALL.GPU -> RED -> poll -> acquire fence -> TMA round trip, ~3.6k of
+// the 8.8k cycles of a forward step.  In the LL variants the streamed fp16 operand buffer is pre-filled with the
+// bit pattern 0xFFFF (an fp16 NaN that neither h in (-1,1) nor a saturated gate gradient can produce); producers
+// store their values with relaxed gpu-scope stores and NOTHING else, consumers poll the 16-byte packets they need
+// with relaxed gpu-scope loads until no 2-byte element equals the sentinel (every element is its own flag, so
+// torn 16-byte packets are harmless) and copy them into the 128B-swizzled K-major tile the MMA reads.  No fence, no
+// atomic, no barrier counter on the critical path; one L2 round trip from "stored" to "in shared memory".
+constexpr unsigned int LL_SENTINEL = 0xFFFFFFFFu;
+__device__ __forceinline__ uint4 ld_relaxed_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_v2(void* p, unsigned int a, unsigned int b) {
+  asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ bool ll_ready(const uint4& v) {
+  return (__vcmpeq2(v.x, LL_SENTINEL) | __vcmpeq2(v.y, LL_SENTINEL) | __vcmpeq2(v.z, LL_SENTINEL) |
+          __vcmpeq2(v.w, LL_SENTINEL)) == 0u;
+}
+// poll one packet until it is complete; bounded (a protocol fault sets *err and lets the kernel run to its end)
+__device__ __forceinline__ void ll_wait(uint4& v, const void* src, int* err) {
+  if (ll_ready(v)) return;
+  const long long t0 = clock64();
+  unsigned int it = 0;
+  do {
+    v = ld_relaxed_v4(src);
+    if ((++it & 63u) == 0) {
+      if (*(volatile int*)err) return;
+      if (clock64() - t0 > rp::SPIN_LIMIT) {
+        *(volatile int*)err = 1;
+        printf("ds2: recurrent sweep data-flag timeout (block %d)\n", blockIdx.x);
+        return;
+      }
+    }
+  } while (!ll_ready(v));
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ void st_relaxed_u32(void* p, unsigned int v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// poll one 32-bit word until it differs from the sentinel (bounded like ll_wait)
+__device__ __forceinline__ unsigned int ll_wait_u32(const unsigned int* src, int* err) {
+  unsigned int v = ld_relaxed(src);
+  if (v != LL_SENTINEL) return v;
+  const long long t0 = clock64();
+  unsigned int it = 0;
+  do {
+    v = ld_relaxed(src);
+    if ((++it & 63u) == 0) {
+      if (*(volatile int*)err) return 0u;
+      if (clock64() - t0 > rp::SPIN_LIMIT) { *(volatile int*)err = 1; return 0u; }
+    }
+  } while (v == LL_SENTINEL);
+  return v;
+}
+
 
 // RES = true: "resident" variant.  W_hh is converted to fp16 once per call and this CTA's slice
 // (G*16 rows x H, 128 KB at H=1024) stays in shared memory for the whole sweep; per step only the
@@ -587,8 +651,9 @@ size_t rnn_sweep_tc_workspace_bytes(int rnn, int T, int B, int H, int D) {
   const int G = rnn == DS2_RNN_LSTM ? 4 : (rnn == DS2_RNN_GRU ? 3 : 1);
   const size_t fwd = 4096 + align_up((size_t)D * G * H * H * 2, 256) + align_up((size_t)D * T * B * H * 2, 256);
   const size_t GH = (size_t)G * H;
-  const size_t bwd = 4096 + align_up((size_t)D * (T + 1) * 4, 256) + align_up((size_t)D * H * GH * 2, 256) +
-                     align_up((size_t)T * B * D * GH * 2, 256);
+  const size_t bwd = 4096 + align_up((size_t)D * (T + 1) * 4, 256) + align_up((size_t)T * 4, 256) +
+                     align_up((size_t)D * T * (H / 16 + 1) * 4 * 4, 256) + align_up((size_t)D * H * GH * 2, 256) +
+                     align_up((size_t)T * B * D * GH * 2, 256);   // >= splitk_res_ws_bytes()
   return (fwd > bwd ? fwd : bwd) + 256;
 }
 
@@ -686,7 +751,7 @@ static int launch_fwd_resident(const SeqArgs& a, void* ws, size_t ws_bytes, cuda
   return DS2_OK;
 }
 
-template <int RNN>
+template <int RNN, bool LL>
 static int launch_fwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st);
 
 template <int RNN>
@@ -695,7 +760,10 @@ static int launch_fwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t 
   const int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
   if (!getenv("DS2_NO_RESIDENT")) {
     if (RNN != DS2_RNN_TANH && env_flag("DS2_FWD_SPLITK", 1)) {   // 2-CTA clusters, half the MMA chain per step
-      int rc = launch_fwd_splitk<RNN == DS2_RNN_TANH ? DS2_RNN_LSTM : RNN>(a, ws, ws_bytes, st);
+      constexpr int R = RNN == DS2_RNN_TANH ? DS2_RNN_LSTM : RNN;
+      // DS2_FWD_LL=0: grid barrier + TMA of h_{t-1} (round 1) instead of the flag-in-data exchange
+      int rc = env_flag("DS2_FWD_LL", 1) ? launch_fwd_splitk<R, true>(a, ws, ws_bytes, st)
+                                         : launch_fwd_splitk<R, false>(a, ws, ws_bytes, st);
       if (rc != 1) return rc;
     }
     int rc = launch_fwd_resident<RNN>(a, ws, ws_bytes, st);
@@ -1023,10 +1091,13 @@ __device__ __forceinline__ float pow2f(int ex) { return __int_as_float((ex + 127
 
 // CL = CTAs per cluster = K split: 4 (64 units per cluster, MMA M = 64) or 8 (128 units, M = 128: the same
 // number of CTAs, but each reduces only K/8, i.e. half as many MMA instructions on the per-step critical path).
-template <int RNN, bool RES, int CL>
+// LL (RES only): no grid barrier; the scaled fp16 gate gradients are their own ready flags (see the LL helpers) and
+// the per-step maxima travel as one word per (CTA, epilogue warp) in `gmeta`.
+template <int RNN, bool RES, int CL, bool LL = false>
 __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __grid_constant__ PersistParams p) {
   using namespace rp;
   using namespace tc;
+  static_assert(!LL || RES, "the flag-in-data exchange streams the fp16 copy of the resident variant");
   constexpr int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
   constexpr int UM = UT * CL;                  // units per cluster (all M rows valid): 64 or 128 = MMA M
   constexpr int A_BYTES = UM * 128;            // one K chunk of the weight tile (shadows rp::A_BYTES)
@@ -1042,7 +1113,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
   float* cst = part + CL * xt_slice(UT, NB);                             // [16][NBp] carried dc / dh
   int* lens_s = reinterpret_cast<int*>(cst + UT * NBp);
   unsigned int* cta_max = reinterpret_cast<unsigned int*>(lens_s + ((NB + 1) & ~1));   // [2] (8 bytes)
-  uint64_t* full = reinterpret_cast<uint64_t*>(cta_max + 2);             // resident: one per group of 4 chunks
+  unsigned int* wmax = cta_max + 2;                                      // LL: [2 step parities][4 epilogue warps]
+  uint64_t* full = reinterpret_cast<uint64_t*>(cta_max + 10);            // resident: one per group of 4 chunks
   uint64_t* empty = full + (RES ? 32 : STAGES);                          // resident: [0] = weights landed
   uint64_t* accum_bar = empty + STAGES;
   uint64_t* part_bar = accum_bar + 1;
@@ -1062,16 +1134,25 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmW[d]);
-    tma_prefetch_desc(&p.tmV[d]);
-    for (int i = 0; i < (RES ? 32 : STAGES); ++i) mbar_init(&full[i], 1);
+    if (!LL) tma_prefetch_desc(&p.tmV[d]);
+    for (int i = 0; i < (RES ? 32 : STAGES); ++i) mbar_init(&full[i], LL ? 4 : 1);   // LL: one arrival per loader warp
     for (int i = 0; i < STAGES; ++i) mbar_init(&empty[i], 1);
     mbar_init(accum_bar, 1);
     mbar_init(part_bar, 1);
     fence_barrier_init();
     cta_max[0] = 0u;
+    for (int i = 0; i < 8; ++i) wmax[i] = 0u;
   }
   for (int i = threadIdx.x; i < UT * NBp; i += THREADS) cst[i] = 0.f;
   for (int i = threadIdx.x; i < NB; i += THREADS) lens_s[i] = i < B ? p.len[i] : 0;
+  if (LL) {   // batch-padding rows of the streamed tile are never loaded: keep them finite (their columns are unused)
+    uint8_t* vb = smem + NKR * A_BYTES;
+    for (int i = threadIdx.x; i < NKR * (NB - B) * 8; i += THREADS) {
+      const int c = i / ((NB - B) * 8), r = B + (i / 8) % (NB - B), j = i % 8;
+      *reinterpret_cast<uint4*>(vb + c * B_BYTES + r * 128 + j * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
+  }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
@@ -1093,7 +1174,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
         mbar_arrive_expect_tx(&empty[0], (uint32_t)(NKR * UM * 128));
         for (int c = 0; c < NKR; ++c) tma_load_2d(smem + c * A_BYTES, &p.tmW[d], &empty[0], kbase + c * 64, ut * UM);
         uint8_t* vbuf = smem + NKR * A_BYTES;
-        for (int step = 1; step < T; ++step) {
+        for (int step = 1; !LL && step < T; ++step) {     // LL: the epilogue warps fetch dGh[t_next] themselves
           const int t = d == 0 ? T - 1 - step : step;
           const int tn = d == 0 ? t + 1 : t - 1;
           grid_wait_counter(ctr, n_arrive * (unsigned int)step, p.err);
@@ -1221,13 +1302,19 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
 #pragma unroll
       for (int j = 0; j < 4; ++j) bsum[i][j] = 0.f;
     int sx_prev = 0, sx_cur = 0;
-    if (RES) sx_cur = pow2_exp_for(ld_acquire(gmax_d), 0);
+    // step-0 scale: |dGh| <= |dh| = |dY[t_first]| for every cell type
+    if (RES) sx_cur = pow2_exp_for(__ldg(p.dymax + (d == 0 ? T - 1 : 0)), 0);
     float s_cur = pow2f(sx_cur), inv_prev = 1.f;
+    const int cta_in_dir = ut * CL + ks, nmeta = NTc * CL * 4;
+    (void)gmax_d;
     for (int step = 0; step < T; ++step) {
       const int t = d == 0 ? T - 1 - step : step;
       const int tp = d == 0 ? t - 1 : t + 1;
       const bool tp_in = tp >= 0 && tp < T;
       float lmax = 0.f;
+      // the scale of this step's outputs must also cover this step's own upstream gradient: a frame of dY far above
+      // its neighbours would otherwise saturate the fp16 copy (the previous step's maximum knows nothing of it)
+      const unsigned int dym = RES ? __ldg(p.dymax + t) : 0u;
       // Saved activations / states / dY of this step do not depend on the recurrence, and every gate gradient is
       // linear in dh (LSTM: in dh and dc): fetch them and reduce them to per-pair coefficients BEFORE waiting for
       // the MMAs, so that global-load and special-function latencies hide behind the tensor-core phase and only
@@ -1300,9 +1387,18 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
         mbar_wait(accum_bar, acc_phase);
         tc_fence_after();
         if (RES) {
-          // this step's MMAs ran, so the grid barrier was passed: the maximum of step-1 the producer forwarded is final
+          // non-LL: this step's MMAs ran, so the grid barrier was passed: the maximum of step-1 the producer forwarded
+          // is final.  LL: the four loader warps left the maximum over all (CTA, warp) words of step-1 in wmax[parity]
+          // before their last full-barrier arrival (ordered by the full -> MMA -> accumulator barrier chain).
+          unsigned int gm;
+          if (LL) {
+            const volatile unsigned int* wm = wmax + (step & 1) * 4;
+            gm = max(max(wm[0], wm[1]), max(wm[2], wm[3]));
+          } else {
+            gm = *(volatile unsigned int*)(cta_max + 1);
+          }
           sx_prev = sx_cur;
-          sx_cur = pow2_exp_for(*(volatile unsigned int*)(cta_max + 1), sx_prev);
+          sx_cur = pow2_exp_for(max(gm, dym), sx_prev);      // non-negative floats order like their bit patterns
           s_cur = pow2f(sx_cur);
           inv_prev = pow2f(-sx_prev);
         }
@@ -1348,7 +1444,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
         uint2 pk;
         pk.x = *reinterpret_cast<const unsigned int*>(&lo);
         pk.y = *reinterpret_cast<const unsigned int*>(&hi);
-        *reinterpret_cast<uint2*>(dst) = pk;
+        if (LL) st_relaxed_v2(dst, pk.x, pk.y);            // saturated at +-65000: never the 0xFFFF sentinel
+        else *reinterpret_cast<uint2*>(dst) = pk;
       };
       auto finish4 = [&](int b, const float (&k)[6][NPF], const float (&dyv)[NPF], bool valid, float (&o)[5][NPF]) {
 #pragma unroll
@@ -1360,7 +1457,10 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
         if (!valid) {
           if (RES) {
 #pragma unroll
-            for (int g = 0; g < G; ++g) *reinterpret_cast<uint2*>(hp16 + g * H) = make_uint2(0u, 0u);
+            for (int g = 0; g < G; ++g) {
+              if (LL) st_relaxed_v2(hp16 + g * H, 0u, 0u);
+              else *reinterpret_cast<uint2*>(hp16 + g * H) = make_uint2(0u, 0u);
+            }
           }
           return;
         }
@@ -1424,8 +1524,49 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
         for (int g = 0; g < G; ++g) st4(gp + g * H, o[g]);
         if (RNN == DS2_RNN_GRU) st4(p.aux + (((size_t)d * T + t) * B + b) * H + u0 + uq, o[4]);
       };
+      // LL: fetch the scaled fp16 gate gradients dGh[t] of ALL units of this CTA's K range (written by every CTA of
+      // the direction) into the swizzled K-major tile of the next step's MMAs; same packet / group scheme as the
+      // forward sweep (fetch_h).  Before the last group is handed over, the per-(CTA, warp) maxima of the step are
+      // polled too and their maximum is left in wmax[next parity][warp] for the scale of the next step.
+      auto fetch_dg = [&](int t_src) {
+        const size_t ld = (size_t)D * GH;
+        const __half* src = p.dg16 + (size_t)t_src * B * ld + (size_t)d * GH + kbase;
+        const uint32_t vb = smem_u32(smem + NKR * A_BYTES);
+        for (int g = 0; g < NG; ++g) {
+          const int c0 = grp_begin(g), c1 = min(NKR, grp_begin(g + 1));
+          const int npk = (c1 - c0) * 8, total = B * npk;
+          for (int base = 0; base < total; base += 128 * 8) {
+            uint4 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int idx = base + k * 128 + e;
+              if (idx < total) v[k] = ld_relaxed_v4(src + (size_t)(idx / npk) * ld + (size_t)(c0 * 8 + idx % npk) * 8);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int idx = base + k * 128 + e;
+              if (idx < total) {
+                const int row = idx / npk, pc = c0 * 8 + idx % npk;
+                ll_wait(v[k], src + (size_t)row * ld + (size_t)pc * 8, p.err);
+                st_shared_v4(vb + (uint32_t)((pc >> 3) * B_BYTES + row * 128 + (((pc & 7) ^ (row & 7)) << 4)), v[k]);
+              }
+            }
+          }
+          if (g == NG - 1) {
+            const unsigned int* mp = p.gmeta + ((size_t)d * T + step) * nmeta;
+            unsigned int m = 0u;
+            for (int i = e; i < nmeta; i += 128) m = max(m, ll_wait_u32(mp + i, p.err));
+            m = __reduce_max_sync(0xffffffffu, m);
+            if (lane == 0) wmax[((step + 1) & 1) * 4 + q] = m;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full + g);
+          if (e == 0 && g == 0) trace_stamp(p.trace, p.T, step + 1, 1);
+        }
+      };
       // the non-resident variants stream the fp32 gate gradients themselves: nothing can be deferred there
-      const bool defer = RES && p.defer && single;
+      const bool defer = RES && (LL || p.defer) && single;
       float sv[5][NPF];
       if (single) {
         finish4(b_own, kc, pdy, pvalid, sv);
@@ -1440,19 +1581,30 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
       if (RES) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-        if (lane == 0) atomicMax(cta_max, __float_as_uint(lmax));     // non-negative floats order like uints
+        if (LL) {           // one word per (CTA, epilogue warp): no intra-CTA reduction on the critical path
+          unsigned int lb = __float_as_uint(lmax);
+          if (lb >= 0x7f800000u) lb = 0x7f7fffffu;                    // inf / nan: finite, and never the sentinel
+          if (lane == 0) st_relaxed_u32(p.gmeta + ((size_t)d * T + step) * nmeta + cta_in_dir * 4 + q, lb);
+        } else if (lane == 0) {
+          atomicMax(cta_max, __float_as_uint(lmax));                  // non-negative floats order like uints
+        }
       }
       if (e == 0) trace_stamp(p.trace, p.T, step, 8);
-      named_bar_sync(1, 128);
-      if (e == 0) {
-        trace_stamp(p.trace, p.T, step, 9);
-        if (RES) {
-          atomicMax(p.gmax + (size_t)d * (T + 1) + step + 1, cta_max[0]);
-          cta_max[0] = 0u;
+      if (!LL) {
+        named_bar_sync(1, 128);
+        if (e == 0) {
+          trace_stamp(p.trace, p.T, step, 9);
+          if (RES) {
+            atomicMax(p.gmax + (size_t)d * (T + 1) + step + 1, cta_max[0]);
+            cta_max[0] = 0u;
+          }
+          fence_proxy_async_global();
+          trace_stamp(p.trace, p.T, step, 10);
+          red_release(ctr, 1u);
+          trace_stamp(p.trace, p.T, step, 11);
+          trace_stamp_ns(p.trace, p.T, step, 12);
         }
-        fence_proxy_async_global();
-        trace_stamp(p.trace, p.T, step, 10);
-        red_release(ctr, 1u);
+      } else if (e == 0) {
         trace_stamp(p.trace, p.T, step, 11);
         trace_stamp_ns(p.trace, p.T, step, 12);
       }
@@ -1460,24 +1612,35 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
         if (b_own < B) store_dg(b_own, sv);
         if (e == 0) trace_stamp(p.trace, p.T, step, 13);
       }
+      if (LL && step + 1 < T) {        // the other CTAs' gate gradients land while the fp32 stores above drain
+        if (e == 0) trace_stamp(p.trace, p.T, step + 1, 0);
+        fetch_dg(t);
+      }
     }
     if (p.dbias[d]) {
       // lanes with equal (lane & 3) hold the same 4 units for different batch columns: reduce over lane bits 2..4,
-      // then one atomic per (gate, unit) and warp
+      // then the four warps through shared memory in a fixed order (the exchange tiles are free now).  Every
+      // (gate, unit) of these 16 units belongs to this CTA alone: plain stores, bit-repeatable, no atomics.
+      named_bar_sync(1, 128);                              // everybody is done reading `part`
+      float* red = part;                                   // [4 warps][5][16]
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
-        if (i >= G && !(RNN == DS2_RNN_GRU && i == 4)) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float v = bsum[i][j];
           v += __shfl_xor_sync(0xffffffffu, v, 4);
           v += __shfl_xor_sync(0xffffffffu, v, 8);
           v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (lane < 4) {
-            if (i < G) atomicAdd(&p.dbias[d][(size_t)i * H + u0 + 4 * lane + j], v);
-            else atomicAdd(&p.dbias_hn[d][u0 + 4 * lane + j], v);
-          }
+          if (lane < 4) red[(q * 5 + i) * 16 + 4 * lane + j] = v;
         }
+      }
+      named_bar_sync(1, 128);
+      if (e < 80) {
+        const int i = e / 16, u = e % 16;
+        const float v = (red[(0 * 5 + i) * 16 + u] + red[(1 * 5 + i) * 16 + u]) +
+                        (red[(2 * 5 + i) * 16 + u] + red[(3 * 5 + i) * 16 + u]);
+        if (i < G) p.dbias[d][(size_t)i * H + u0 + u] = v;
+        else if (RNN == DS2_RNN_GRU && i == 4) p.dbias_hn[d][u0 + u] = v;
       }
     }
   }
@@ -1495,7 +1658,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
 // epilogue warp pushes its 32 accumulator rows into the owner's shared memory with st.async (complete_tx on
 // the owner's mbarrier); the owner adds the two partial tiles, the input projection and the biases, and runs
 // gates + cell update for its 16 units in one pass (thread = 4 consecutive units x one batch column).
-template <int RNN>
+template <int RNN, bool LL>
 __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __grid_constant__ PersistParams p) {
   using namespace rp;
   using namespace tc;
@@ -1528,8 +1691,8 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmW[d]);
-    tma_prefetch_desc(&p.tmV[d]);
-    for (int i = 0; i < 8; ++i) mbar_init(&full[i], 1);
+    if (!LL) tma_prefetch_desc(&p.tmV[d]);
+    for (int i = 0; i < 8; ++i) mbar_init(&full[i], LL ? 4 : 1);   // LL: one arrival per loader (= epilogue) warp
     mbar_init(wbar, 1);
     mbar_init(accum_bar, 1);
     mbar_init(part_bar, 1);
@@ -1537,6 +1700,14 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __
   }
   for (int i = threadIdx.x; i < UT * NBp; i += THREADS) cst[i] = 0.f;
   for (int i = threadIdx.x; i < NB; i += THREADS) lens_s[i] = i < B ? p.len[i] : 0;
+  if (LL) {   // batch-padding rows of the streamed tile are never loaded: keep them finite (their columns are unused)
+    uint8_t* hb = smem + NKR * AW;
+    for (int i = threadIdx.x; i < NKR * (NB - B) * 8; i += THREADS) {
+      const int c = i / ((NB - B) * 8), r = B + (i / 8) % (NB - B), j = i % 8;
+      *reinterpret_cast<uint4*>(hb + c * B_BYTES + r * 128 + j * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
+  }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
@@ -1558,7 +1729,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __
         tma_load_3d(smem + c * AW + 64 * 128, &p.tmW[d], wbar, (kc0 + c) * 64, U0 + UT, 0);
       }
       uint8_t* hbuf = smem + NKR * AW;
-      for (int step = 1; step < T; ++step) {
+      for (int step = 1; !LL && step < T; ++step) {       // LL: the epilogue warps fetch h_{t-1} themselves (below)
         const int t = d == 0 ? step : T - 1 - step;
         const int tp = d == 0 ? t - 1 : t + 1;
         grid_wait_counter(ctr, n_arrive * (unsigned int)step, p.err);
@@ -1635,6 +1806,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __
     auto st4 = [](float* dst, const float (&v)[4]) { *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]); };
     uint32_t acc_phase = 0, part_phase = 0;
     const bool single = B <= 32;
+    int step_for_trace = 0;
     for (int step = 0; step < T; ++step) {
       const int t = d == 0 ? step : T - 1 - step;
       // input projections of this thread's cells: independent of the recurrence, fetched before the MMA wait
@@ -1739,7 +1911,9 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __
         uint2 pk;
         pk.x = *reinterpret_cast<const unsigned int*>(&lo);
         pk.y = *reinterpret_cast<const unsigned int*>(&hi);
-        *reinterpret_cast<uint2*>(p.h16 + (((size_t)d * T + t) * B + b) * H + u0 + uq) = pk;
+        __half* hdst = p.h16 + (((size_t)d * T + t) * B + b) * H + u0 + uq;
+        if (LL) st_relaxed_v2(hdst, pk.x, pk.y);          // the values are their own ready flags (|h| < 1: never 0xFFFF)
+        else *reinterpret_cast<uint2*>(hdst) = pk;
       };
       auto store4 = [&](int b, const float (&o)[6][4]) {
         const size_t so = (((size_t)d * T + t) * B + b) * H + u0 + uq;
@@ -1751,7 +1925,42 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __
         }
         st4(p.hseq + so, o[5]);
       };
-      const bool defer = p.defer && single;
+      // LL: fetch h_t of ALL units of this CTA's K half (written by the 32 owner CTAs of those units) into the
+      // swizzled K-major tile of the next step's MMA.  Called by the 128 epilogue threads after accum_bar of this
+      // step completed, i.e. when the MMAs that read the tile are done.  One 16-byte packet = 8 consecutive k of
+      // one batch row; consecutive threads take consecutive packets of a row (512 contiguous bytes per warp
+      // instruction); up to 8 polls in flight per thread; a group of 4 K chunks is handed to the MMA thread as soon
+      // as it is complete (fence.proxy.async: generic-proxy stores -> async-proxy reads of tcgen05.mma).
+      auto fetch_h = [&](int t_src) {
+        const __half* src = p.h16 + ((size_t)d * T + t_src) * B * H + (size_t)kc0 * 64;
+        const uint32_t hb = smem_u32(smem + NKR * AW);
+        for (int g = 0; g < NG; ++g) {
+          const int c0 = grp_begin(g), c1 = min(NKR, grp_begin(g + 1));
+          const int npk = (c1 - c0) * 8, total = B * npk;
+          for (int base = 0; base < total; base += 128 * 8) {
+            uint4 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int idx = base + k * 128 + e;
+              if (idx < total) v[k] = ld_relaxed_v4(src + (size_t)(idx / npk) * H + (size_t)(c0 * 8 + idx % npk) * 8);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int idx = base + k * 128 + e;
+              if (idx < total) {
+                const int row = idx / npk, pc = c0 * 8 + idx % npk;
+                ll_wait(v[k], src + (size_t)row * H + (size_t)pc * 8, p.err);
+                st_shared_v4(hb + (uint32_t)((pc >> 3) * B_BYTES + row * 128 + (((pc & 7) ^ (row & 7)) << 4)), v[k]);
+              }
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full + g);
+          if (e == 0 && g == 0) trace_stamp(p.trace, p.T, step_for_trace, 1);
+        }
+      };
+      const bool defer = LL || (p.defer && single);
       float sv[6][4];
       if (single) {
         if (b_own < B) {
@@ -1767,18 +1976,28 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __
         }
       }
       if (e == 0) trace_stamp(p.trace, p.T, step, 8);
-      named_bar_sync(1, 128);          // CTA-scope: every epilogue thread's stores happen-before thread 0's release
-      if (e == 0) {
-        trace_stamp(p.trace, p.T, step, 9);
-        fence_proxy_async_global();
-        trace_stamp(p.trace, p.T, step, 10);
-        red_release(ctr, 1u);
+      if (!LL) {
+        named_bar_sync(1, 128);        // CTA-scope: every epilogue thread's stores happen-before thread 0's release
+        if (e == 0) {
+          trace_stamp(p.trace, p.T, step, 9);
+          fence_proxy_async_global();
+          trace_stamp(p.trace, p.T, step, 10);
+          red_release(ctr, 1u);
+          trace_stamp(p.trace, p.T, step, 11);
+          trace_stamp_ns(p.trace, p.T, step, 12);
+        }
+      } else if (e == 0) {
         trace_stamp(p.trace, p.T, step, 11);
         trace_stamp_ns(p.trace, p.T, step, 12);
       }
-      if (defer) {
+      if (defer && single) {
         if (b_own < B) store4(b_own, sv);
         if (e == 0) trace_stamp(p.trace, p.T, step, 13);
+      }
+      if (LL && step + 1 < T) {        // the other CTAs' h_t lands while the fp32 stores above drain
+        step_for_trace = step + 1;
+        if (e == 0) trace_stamp(p.trace, p.T, step + 1, 0);
+        fetch_h(t);
       }
     }
   }
@@ -1796,7 +2015,7 @@ static size_t fwd_splitk_smem_bytes(int NB, int H) {
 }
 
 // returns 1 when the shape / device does not take this variant (the caller then uses the 16-unit resident kernel)
-template <int RNN>
+template <int RNN, bool LL>
 static int launch_fwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
   using namespace rp;
   constexpr int G = RNN == DS2_RNN_LSTM ? 4 : 3;
@@ -1817,7 +2036,7 @@ static int launch_fwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
   p.h16 = reinterpret_cast<__half*>(static_cast<char*>(ws) + 4096 + align_up((size_t)a.D * G * a.H * a.H * 2, 256));
   const size_t smem = one_cta_per_sm(fwd_splitk_smem_bytes(p.NB, a.H));
   if (smem > 227 * 1024) return 1;
-  auto kern = rnn_fwd_splitk_kernel<RNN>;
+  auto kern = rnn_fwd_splitk_kernel<RNN, LL>;
   static DeviceOnce attr_once;
   if (attr_once.first()) {
     DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1862,6 +2081,8 @@ static int launch_fwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
     }
   }
   DS2_CHECK_CUDA(cudaMemsetAsync(ws, 0, 4096, st));
+  if (LL)   // every 2-byte element of the h stream is its own "not yet written" flag
+    DS2_CHECK_CUDA(cudaMemsetAsync(p.h16, 0xFF, (size_t)a.D * a.T * a.B * a.H * sizeof(__half), st));
   for (int li = 0; li < launches; ++li) {
     p.d0 = li;
     cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
@@ -1881,7 +2102,7 @@ static size_t splitk_smem_bytes(int NB, int CL) {
   using namespace rp;
   size_t NBp = NB + 1;
   return 1024 + (size_t)STAGES * ((size_t)UT * CL * 128 + (size_t)NB * 128) +
-         ((size_t)CL * xt_slice(UT, NB) + UT * NBp + NB + 8) * sizeof(float) + (2 * STAGES + 3) * sizeof(uint64_t) + 64;
+         ((size_t)CL * xt_slice(UT, NB) + UT * NBp + NB + 16) * sizeof(float) + (2 * STAGES + 3) * sizeof(uint64_t) + 64;
 }
 
 // max |x| over n floats -> atomicMax on float bits (x >= 0 after fabs)
@@ -1894,20 +2115,42 @@ __global__ void absmax_kernel(size_t n, const float* __restrict__ x, unsigned in
   if (threadIdx.x % 32 == 0) atomicMax(out, __float_as_uint(m));
 }
 
+// out[t] = float bits of max |x[t, :]| over the n floats of row t (one CTA per row, x >= 0 after fabs -> uint order)
+__global__ void absmax_rows_kernel(size_t n, const float* __restrict__ x, unsigned int* __restrict__ out) {
+  __shared__ float red[8];
+  const float* row = x + (size_t)blockIdx.x * n;
+  float m = 0.f;
+  for (size_t i = threadIdx.x * 4; i + 3 < n; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  for (size_t i = (n & ~(size_t)3) + threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(row[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x / 32); ++w) m = fmaxf(m, red[w]);
+    out[blockIdx.x] = __float_as_uint(m);
+  }
+}
+
 static size_t splitk_res_smem_bytes(int NB, int Kc, int CL) {
   using namespace rp;
   size_t NBp = NB + 1;
   return 1024 + (size_t)(Kc / 64) * ((size_t)UT * CL * 128 + (size_t)NB * 128) +
-         ((size_t)CL * xt_slice(UT, NB) + UT * NBp + NB + 8) * sizeof(float) + (32 + STAGES + 3) * sizeof(uint64_t) + 64;
+         ((size_t)CL * xt_slice(UT, NB) + UT * NBp + NB + 16) * sizeof(float) + (32 + STAGES + 3) * sizeof(uint64_t) + 64;
 }
 // workspace of the resident backward: [4 KB control][gmax D*(T+1) uints][W^T fp16: D*H*GH][dg16: T*B*D*GH]
+// (+ [dymax: T uints][gmeta: D*T*(H/16)*4 uints] after gmax: H/16 CTAs per direction, 4 epilogue warps each)
 static size_t splitk_res_ws_bytes(int G, int T, int B, int H, int D) {
   const size_t GH = (size_t)G * H;
-  return 4096 + align_up((size_t)D * (T + 1) * 4, 256) + align_up((size_t)D * H * GH * 2, 256) +
+  return 4096 + align_up((size_t)D * (T + 1) * 4, 256) + align_up((size_t)T * 4, 256) +
+         align_up((size_t)D * T * (H / 16) * 4 * 4, 256) + align_up((size_t)D * H * GH * 2, 256) +
          align_up((size_t)T * B * D * GH * 2, 256);
 }
 
-template <int RNN, int CL>
+template <int RNN, int CL, bool LL>
 static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
   using namespace rp;
   const int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
@@ -1930,11 +2173,15 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
   p.bar = reinterpret_cast<unsigned int*>(base + 128);
   size_t off = 4096;
   p.gmax = reinterpret_cast<unsigned int*>(base + off); off += align_up((size_t)a.D * (a.T + 1) * 4, 256);
+  p.dymax = reinterpret_cast<unsigned int*>(base + off); off += align_up((size_t)a.T * 4, 256);
+  p.gmeta = reinterpret_cast<unsigned int*>(base + off);
+  const size_t gmeta_bytes = (size_t)a.D * a.T * (a.H / 16) * 4 * 4;
+  off += align_up(gmeta_bytes, 256);
   __half* wT16 = reinterpret_cast<__half*>(base + off); off += align_up((size_t)a.D * a.H * GH * 2, 256);
   p.dg16 = reinterpret_cast<__half*>(base + off);
   const size_t smem = one_cta_per_sm(splitk_res_smem_bytes(p.NB, GH / CL, CL));
   if (smem > 227 * 1024) return 1;
-  auto kern = rnn_bwd_splitk_kernel<RNN, true, CL>;
+  auto kern = rnn_bwd_splitk_kernel<RNN, true, CL, LL>;
   static DeviceOnce attr_once;
   if (attr_once.first()) {
     DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1979,10 +2226,12 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
       rc = make_tmap_f16(&p.tmV3[d], p.dg16, 3, 64, a.T * a.B, a.D * GH / 64, (size_t)a.D * GH, 64, 64, p.NB, 4);
       if (rc) return rc;
     }
-    // step-0 scale: |dGh| <= |dh| = |dY[t_first]| for every cell type
-    const int t_first = d == 0 ? a.T - 1 : 0;
-    DS2_LAUNCH(absmax_kernel, 64, 256, 0, st, (size_t)a.B * a.H, a.dy + (size_t)t_first * a.B * a.H,
-               p.gmax + (size_t)d * (a.T + 1));
+  }
+  // per-time-step max |dY[t]|: the step-0 scale, and part of every later step's scale (spiky upstream gradients)
+  DS2_LAUNCH(absmax_rows_kernel, a.T, 256, 0, st, (size_t)a.B * a.H, a.dy, p.dymax);
+  if (LL) {   // every 2-byte element of the gate-gradient stream / every word of the maxima is its own ready flag
+    DS2_CHECK_CUDA(cudaMemsetAsync(p.gmeta, 0xFF, gmeta_bytes, st));
+    DS2_CHECK_CUDA(cudaMemsetAsync(p.dg16, 0xFF, (size_t)a.T * a.B * a.D * GH * sizeof(__half), st));
   }
   for (int li = 0; li < launches; ++li) {
     p.d0 = li;
@@ -2006,7 +2255,9 @@ static int launch_bwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
   const int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
   const int GH = G * a.H;
   if (!getenv("DS2_NO_RESIDENT")) {
-    int rc = launch_bwd_splitk_resident<RNN, CL>(a, ws, ws_bytes, st);
+    // DS2_BWD_LL=0: grid barrier + TMA of dGh[t_next] (round 1) instead of the flag-in-data exchange
+    int rc = env_flag("DS2_BWD_LL", 1) ? launch_bwd_splitk_resident<RNN, CL, true>(a, ws, ws_bytes, st)
+                                       : launch_bwd_splitk_resident<RNN, CL, false>(a, ws, ws_bytes, st);
     if (rc != 1) return rc;
   }
   constexpr int UM = UT * CL;

@@ -8,6 +8,7 @@ All inputs must be fp32 CUDA tensors; anything else raises (no eager fallback).
 """
 import ctypes as C
 import functools
+import weakref
 
 import torch
 
@@ -15,6 +16,44 @@ from . import _lib
 from ._lib import RnnDesc, check, get_lib, ptr, ptr_array
 
 _workspaces = {}
+# Gradient sinks: parameter storage address -> the tensor its gradient must be WRITTEN into (a view of the flat
+# gradient buffer, optim.FlatParams).  The C-ABI writes parameter gradients through output pointers anyway; with a
+# sink registered the backward of a block hands it that view instead of a fresh tensor and returns None to autograd,
+# so there is no AccumulateGrad `add` launch per parameter (59 per step at cfg-L) and no temporary.  Semantics with
+# sinks: gradients are overwritten by every backward (one backward per optimizer step), not accumulated.
+_SINKS = {}
+
+
+def register_grad_sinks(params_and_grads):
+    for p, g in params_and_grads:
+        _SINKS[p.data_ptr()] = (weakref.ref(p), g)
+
+
+def clear_grad_sinks():
+    _SINKS.clear()
+
+
+def _sink(t):
+    """the registered gradient view of parameter `t`, or None (also when the entry is stale: the parameter that
+    registered it is gone and the address now belongs to another tensor)"""
+    e = _SINKS.get(t.data_ptr()) if t is not None else None
+    if e is None:
+        return None
+    owner, g = e
+    o = owner()
+    if o is None or o.data_ptr() != t.data_ptr() or g.shape != t.shape or g.device != t.device:
+        if o is None:
+            _SINKS.pop(t.data_ptr(), None)
+        return None
+    return g
+
+
+def _out(sink, like):
+    """(buffer the C call writes the gradient into, value handed back to autograd)"""
+    if sink is not None:
+        return sink, None
+    t = torch.empty_like(like)
+    return t, t
 
 
 def _stream():
@@ -84,6 +123,7 @@ class ConvFrontend(torch.autograd.Function):
                               z1, a1, z2, stats)
         ctx.dims = (B, T)
         ctx.eval_mode = not training
+        ctx.sinks = [_sink(t) for t in (w1, b1, g1, be1, w2, b2, g2, be2)]
         return y
 
     @staticmethod
@@ -97,16 +137,15 @@ class ConvFrontend(torch.autograd.Function):
         B, T = ctx.dims
         dy = _req(dy, "dy")
         dev = x.device
-        dw1, db1, dg1, dbe1 = torch.empty_like(w1), torch.empty(32, device=dev), torch.empty(32, device=dev), \
-            torch.empty(32, device=dev)
-        dw2, db2, dg2, dbe2 = torch.empty_like(w2), torch.empty(32, device=dev), torch.empty(32, device=dev), \
-            torch.empty(32, device=dev)
+        outs = [_out(sk, like) for sk, like in zip(ctx.sinks, (w1, g1, g1, g1, w2, g2, g2, g2))]
+        (dw1, db1, dg1, dbe1, dw2, db2, dg2, dbe2), rets = zip(*outs)
         ws = workspace(lib.ds2_conv_frontend_workspace_bytes(B, T), dev)
         check(lib.ds2_conv_frontend_bwd(B, T, ptr(x), ptr(out_len), ptr(w1), ptr(g1), ptr(be1), ptr(w2), ptr(g2),
                                         ptr(be2), ptr(z1), ptr(a1), ptr(z2), ptr(stats), ptr(dy), ptr(dw1), ptr(db1),
                                         ptr(dg1), ptr(dbe1), ptr(dw2), ptr(db2), ptr(dg2), ptr(dbe2), ptr(ws),
                                         ws.numel(), _stream()), "ds2_conv_frontend_bwd")
-        return (None, None, dw1, db1, dg1, dbe1, None, None, dw2, db2, dg2, dbe2, None, None, None, None, None)
+        return (None, None, rets[0], rets[1], rets[2], rets[3], None, None, rets[4], rets[5], rets[6], rets[7], None,
+                None, None, None, None)
 
 
 class RnnLayer(torch.autograd.Function):
@@ -140,6 +179,7 @@ class RnnLayer(torch.autograd.Function):
                                     ptr(ws), ws.numel(), _stream()), "ds2_rnn_layer_fwd")
         ctx.desc = desc
         ctx.has_bn = bn_g is not None
+        ctx.sinks = [_sink(bn_g), _sink(bn_b)] + [_sink(w) for w in weights]
         # the C backward assumes zero initial state and batch-statistics BatchNorm, and it turns the saved gate
         # activations into gate gradients in place: anything else must fail loudly instead of returning garbage
         ctx.no_backward = ("forward ran with training=False (no saved gate activations, running-statistics "
@@ -171,9 +211,9 @@ class RnnLayer(torch.autograd.Function):
         dy = _req(dy, "dy")
         dev = x.device
         dx = torch.empty_like(x)
-        dg = torch.empty_like(bn_g) if ctx.has_bn else None
-        db = torch.empty_like(bn_b) if ctx.has_bn else None
-        grads = [torch.empty_like(w) for w in weights]
+        dg, rdg = _out(ctx.sinks[0], bn_g) if ctx.has_bn else (None, None)
+        db, rdb = _out(ctx.sinks[1], bn_b) if ctx.has_bn else (None, None)
+        grads, rgrads = zip(*[_out(sk, w) for sk, w in zip(ctx.sinks[2:], weights)])
         ws = workspace(lib.ds2_rnn_workspace_bytes(C.byref(desc)), dev)
         check(lib.ds2_rnn_layer_bwd(C.byref(desc), ptr(x), ptr(len_dev), ptr(bn_g), ptr(bn_b),
                                     ptr_array(weights[0::4]), ptr_array(weights[1::4]), ptr_array(weights[2::4]),
@@ -181,7 +221,7 @@ class RnnLayer(torch.autograd.Function):
                                     ptr_array(grads[0::4]), ptr_array(grads[1::4]), ptr_array(grads[2::4]),
                                     ptr_array(grads[3::4]), ptr(ws), ws.numel(), _stream()), "ds2_rnn_layer_bwd")
         assert len(grads) == 4 * D
-        return (dx, None, None, None, None, None, None, dg, db, None, None, None, None, *grads)
+        return (dx, None, None, None, None, None, None, rdg, rdb, None, None, None, None, *rgrads)
 
 
 class Lookahead(torch.autograd.Function):
@@ -195,6 +235,7 @@ class Lookahead(torch.autograd.Function):
         y = torch.empty_like(x)
         check(lib.ds2_lookahead_fwd(T, B, H, ctxlen, ptr(x), ptr(w), ptr(y), _stream()), "ds2_lookahead_fwd")
         ctx.save_for_backward(x, w)
+        ctx.sink = _sink(w)
         return y
 
     @staticmethod
@@ -204,10 +245,11 @@ class Lookahead(torch.autograd.Function):
         x, w = ctx.saved_tensors
         T, B, H = x.shape
         dy = _req(dy, "dy")
-        dz, dx, dw = torch.empty_like(x), torch.empty_like(x), torch.empty_like(w)
+        dz, dx = torch.empty_like(x), torch.empty_like(x)
+        dw, rdw = _out(ctx.sink, w)
         check(lib.ds2_lookahead_bwd(T, B, H, w.shape[-1], ptr(x), ptr(w), ptr(dy), ptr(dz), ptr(dx), ptr(dw),
                                     _stream()), "ds2_lookahead_bwd")
-        return dx, dw
+        return dx, rdw
 
 
 class FcHead(torch.autograd.Function):
@@ -230,6 +272,7 @@ class FcHead(torch.autograd.Function):
         ctx.save_for_backward(g, b, w, xhat, stats)
         ctx.dims = (rows, H, Cn, T, B)
         ctx.eval_mode = not training
+        ctx.sinks = [_sink(g), _sink(b), _sink(w)]
         return logits
 
     @staticmethod
@@ -244,11 +287,11 @@ class FcHead(torch.autograd.Function):
         dlogits = _req(dlogits, "dlogits")
         dev = dlogits.device
         dx = torch.empty(T, B, H, device=dev)
-        dg, db, dw = torch.empty_like(g), torch.empty_like(b), torch.empty_like(w)
+        (dg, rdg), (db, rdb), (dw, rdw) = (_out(sk, like) for sk, like in zip(ctx.sinks, (g, b, w)))
         ws = workspace(lib.ds2_fc_head_workspace_bytes(rows, H, Cn), dev)
         check(lib.ds2_fc_head_bwd(rows, H, Cn, ptr(g), ptr(b), ptr(w), ptr(xhat), ptr(stats), ptr(dlogits), ptr(dx),
                                   ptr(dg), ptr(db), ptr(dw), ptr(ws), ws.numel(), _stream()), "ds2_fc_head_bwd")
-        return dx, dg, db, None, None, dw, None, None, None, None
+        return dx, rdg, rdb, None, None, rdw, None, None, None, None
 
 
 class CtcLoss(torch.autograd.Function):

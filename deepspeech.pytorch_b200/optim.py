@@ -15,7 +15,11 @@ _ALIGN = 64  # floats: 256-byte aligned views (TMA / float4 friendly)
 
 
 class FlatParams:
-    def __init__(self, model):
+    """`direct_grads=True` registers every gradient view as the sink of its parameter (ops.register_grad_sinks): the
+    backward kernels then write the gradients straight into `self.grad` (no AccumulateGrad adds, no temporaries, no
+    zero_grad needed — every parameter's gradient is overwritten by every backward)."""
+
+    def __init__(self, model, direct_grads: bool = False):
         params = [p for p in model.parameters() if p.requires_grad]
         dev = params[0].device
         offs, n = [], 0
@@ -29,9 +33,14 @@ class FlatParams:
             self.data[o:o + p.numel()].copy_(p.data.reshape(-1))
             p.data = self.data[o:o + p.numel()].view(p.shape)
             p.grad = self.grad[o:o + p.numel()].view(p.shape)
+        self.direct_grads = bool(direct_grads)
+        if self.direct_grads:
+            from . import ops
+            ops.register_grad_sinks((p, p.grad) for p in params)
 
     def zero_grad(self):
-        self.grad.zero_()
+        if not self.direct_grads:          # with sinks every gradient is overwritten by the next backward
+            self.grad.zero_()
 
 
 class FusedOptimizer:

@@ -182,6 +182,22 @@ int ds2_sgd_nesterov_step(int64_t n, float* p, const float* g, float* momentum_b
                           float weight_decay, int first_step, float grad_scale, float max_norm,
                           float* grad_norm_out, void* norm_ws, void* stream);
 
+/* ---- input pipeline (row N3): raw PCM -> padded, length-sorted spectrogram batch ---------------
+ * Replaces SpectrogramParser.compute_spectrogram (data_loader.py:73-94: librosa.stft(n_fft = win_length, hop,
+ * window, center=True) -> |.| -> log1p -> (x - mean)/std, torch's unbiased std) for every utterance of a batch and
+ * the zero-padding copy of _collate_fn (data_loader.py:247-270).
+ *   wave      concatenated fp32 PCM of the n_utts utterances (device)
+ *   offsets   (n_utts+1) int64 sample offsets into wave (device)
+ *   dst_row   (n_utts) int32: batch row of each utterance (the host sorts by length, descending, stable)
+ *   window    (n_fft) fp32 analysis window (device), e.g. periodic Hamming
+ *   pad_reflect  1: librosa pad_mode="reflect" (librosa < 0.10), 0: "constant" zeros (librosa >= 0.10)
+ *   out       (n_utts, 1, n_fft/2+1, Tmax) fp32, frames t >= 1 + len/hop of a row are written as zeros
+ *   max_samples  length of the longest utterance (grid sizing); Tmax >= max_samples/hop + 1              */
+size_t ds2_spectrogram_workspace_bytes(int n_utts);
+int ds2_spectrogram_batch(int n_utts, const float* wave, const int64_t* offsets, const int32_t* dst_row,
+                          int max_samples, int n_fft, int hop, const float* window, int pad_reflect, int normalize,
+                          float* out, int Tmax, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- dense GEMM used by the blocks above, exported for tests / the roofline bench ------------
  *   C[M,N] = alpha * op(A) op(B) + beta * C ; row-major ; transX: 0 = as stored, 1 = transposed.
  *   Dispatches on ds2_get_precision(): fp32 FFMA kernel or the tcgen05 TF32 kernel.            */

@@ -13,10 +13,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import gpu_diag_rnn as dr  # noqa: E402
 
 SLOTS = 16
-PHASES = [("wait(arrive->pass)", None), ("tma_issue", (0, 1)), ("first_full", (0, 2)), ("mma first->last", (2, 3)),
-          ("commit", (3, 4)), ("accum wake", (4, 5)), ("tmem+act/part", (5, 6)), ("bar1/cluster", (6, 7)),
-          ("combine", (7, 8)), ("bar2", (8, 9)), ("fence/atomic", (9, 10)), ("red.release", (10, 11)),
-          ("deferred stores", (11, 13))]
+# slot pairs (LL sweeps: 0 = operand fetch starts, 1 = first group of 4 K chunks in shared memory; barrier sweeps
+# (DS2_FWD_LL=0 / DS2_BWD_LL=0): 0 = grid barrier passed, 1 = TMA issued, 9..11 = fence / red.release)
+PHASES = [("prev stores(11)->fetch/barrier(0)", None), ("fetch start -> group 0 ready", (0, 1)),
+          ("fetch start -> MMA starts", (0, 2)), ("mma first->last group", (2, 3)), ("last group -> commit", (3, 4)),
+          ("accum wake", (4, 5)), ("tmem + st.async", (5, 6)), ("partials landed", (6, 7)), ("gates/cell", (7, 8)),
+          ("8 -> 11 (barrier variants: fence + red)", (8, 11)), ("deferred fp32 stores", (11, 13))]
 
 
 def trace(rnn, T, B, In, H, ncta_dir):
@@ -54,9 +56,9 @@ def trace(rnn, T, B, In, H, ncta_dir):
 
 def main():
     print(torch.cuda.get_device_name(0))
-    for defer in (0, 1):
-        os.environ["DS2_SWEEP_DEFER"] = str(defer)
-        print(f"=== DS2_SWEEP_DEFER={defer}", flush=True)
+    for ll in (1, 0):
+        os.environ["DS2_FWD_LL"] = os.environ["DS2_BWD_LL"] = str(ll)
+        print(f"=== DS2_FWD_LL = DS2_BWD_LL = {ll}", flush=True)
         for args in [("lstm", True, 30, 32, 128, 256, True), ("gru", True, 25, 7, 64, 256, True),
                      ("rnn", True, 19, 4, 64, 256, False), ("lstm", True, 40, 32, 512, 1024, True)]:
             try:

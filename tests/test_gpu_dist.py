@@ -67,11 +67,12 @@ def _worker(rank, world, port, backend, q):
         loss.backward()
         ex.finish()
         torch.cuda.synchronize()
-        grads = {k: (p.grad.detach() / world).cpu() for k, p in model.named_parameters()}
+        # numpy: pickled by value (torch tensors travel as shared-memory handles that die with this process)
+        grads = {k: (p.grad.detach() / world).cpu().numpy() for k, p in model.named_parameters()}
         opt.step(grad_scale=1.0 / world)
         D.broadcast_buffers(model, src=0)
         torch.cuda.synchronize()
-        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
         q.put((rank, float(loss), grads, sd))
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -112,6 +113,7 @@ def test_two_rank_step_equals_oracle_mean_gradient(backend):
     mean = {k: sum(ref["grads"][k] for ref in refs) / world for k in refs[0]["grads"]}
     for r in range(world):
         for k, g in results[r][2].items():
+            g = torch.from_numpy(g)
             d = float(mean[k].abs().max()) or 1.0
             assert float((g - mean[k]).abs().max()) / d < 2e-3, (r, k)
     # parameters after the fused clip + AdamW step == torch.optim.AdamW on the averaged gradient
@@ -121,7 +123,7 @@ def test_two_rank_step_equals_oracle_mean_gradient(backend):
     torch.nn.utils.clip_grad_norm_(list(leaves.values()), 400.0)
     torch.optim.AdamW(list(leaves.values()), lr=1.5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5).step()
     for r in range(world):
-        sd = results[r][3]
+        sd = {k: torch.from_numpy(v) for k, v in results[r][3].items()}
         for k, p in leaves.items():
             # AdamW's first step moves every weight by ~lr regardless of the gradient scale: compare the UPDATE
             # (where the gradient is far above eps = 1e-8, so that g / (|g| + eps) is insensitive to its last bits)

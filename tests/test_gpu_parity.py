@@ -341,14 +341,15 @@ def _one_layer(rnn, T, B, In, H, seed):
 
 @pytest.mark.parametrize("rnn,B", [("lstm", 32), ("lstm", 20), ("gru", 20), ("lstm", 40), ("gru", 48)])
 def test_tf32_sweep_variants_agree_with_the_fp32_path(rnn, B, monkeypatch):
-    """forward: 2-CTA split-K clusters vs 16-unit CTAs; backward: 8- vs 4-CTA clusters (LSTM, B = 32); stores deferred
-    past the barrier arrival or not.  H = 256 takes every variant; B = 20 exercises the N padding (24 / 32 columns),
+    """forward: 2-CTA split-K clusters vs 16-unit CTAs; backward: 8- vs 4-CTA clusters (LSTM, B = 32); flag-in-data
+    exchange (default) vs grid barrier + TMA (DS2_FWD_LL / DS2_BWD_LL = 0); stores deferred past the barrier or not.  H = 256 takes every variant; B = 20 exercises the N padding (24 / 32 columns),
     B > 32 the second pass of the epilogues over the batch columns."""
     run = _one_layer(rnn, T=33, B=B, In=192, H=256, seed=11)
     ds.set_precision("fp32")
     ref = run()
     ds.set_precision("tf32")
     variants = [{}, {"DS2_FWD_SPLITK": "0"}, {"DS2_SPLITK_CL": "4"}, {"DS2_SWEEP_DEFER": "0"},
+                {"DS2_FWD_LL": "0"}, {"DS2_BWD_LL": "0"}, {"DS2_FWD_LL": "0", "DS2_BWD_LL": "0", "DS2_SPLITK_CL": "4"},
                 {"DS2_FWD_SPLITK": "0", "DS2_SPLITK_CL": "4", "DS2_SWEEP_DEFER": "0"}]
     for env in variants:
         for k_, v in env.items():
@@ -390,3 +391,34 @@ def test_gemm_split_k_accumulates_into_c():
     c0 = torch.randn(M, N, generator=g, device="cuda")
     c1 = ds.ops.gemm(a, b, True, False, out=c0.clone(), alpha=0.5, beta=1.0)
     assert rel_l2(c1, 0.5 * ref + c0.double()) < 1e-3
+
+
+@pytest.mark.parametrize("rnn_type,bidir", [("lstm", True), ("gru", False)])
+def test_direct_gradient_sinks_equal_autograd_accumulation(rnn_type, bidir):
+    """FlatParams(direct_grads=True): every backward kernel writes its parameter gradients straight into the flat
+    buffer (no AccumulateGrad adds).  Must be bit-identical to the autograd route, also on a second step (gradients
+    are overwritten, not accumulated), and a model without sinks must be unaffected by a registry entry whose owner
+    is gone."""
+    from deepspeech_pytorch_b200.optim import FlatParams
+    ocfg = oracle_cfg(rnn_type, bidir, 32, 2, ctx=5)
+    P = O.init_params(ocfg, seed=4)
+    batches = [O.synth_batch(3, 70, seed=s, lmin=3, lmax=8) for s in (1, 2)]
+    grads = {}
+    for direct in (False, True):
+        model = make_model(rnn_type, bidir, 32, 2, ctx=5, params=P).train()
+        flat = FlatParams(model, direct_grads=direct)
+        snaps = []
+        for x, targets, pct, tsz in batches:
+            flat.zero_grad()
+            model.training_step((x.cuda(), targets, pct.clone(), tsz), 0).backward()
+            torch.cuda.synchronize()
+            snaps.append(flat.grad.clone())
+        grads[direct] = snaps
+        del model, flat
+    for a, b in zip(grads[False], grads[True]):
+        assert torch.equal(a, b)
+    assert not torch.equal(grads[True][0], grads[True][1])
+    model = make_model(rnn_type, bidir, 32, 2, ctx=5, params=P).train()       # no FlatParams: plain autograd grads
+    x, targets, pct, tsz = batches[0]
+    model.training_step((x.cuda(), targets, pct.clone(), tsz), 0).backward()
+    assert all(p.grad is not None for p in model.parameters())
