@@ -761,8 +761,11 @@ static int launch_fwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t 
   if (!getenv("DS2_NO_RESIDENT")) {
     if (RNN != DS2_RNN_TANH && env_flag("DS2_FWD_SPLITK", 1)) {   // 2-CTA clusters, half the MMA chain per step
       constexpr int R = RNN == DS2_RNN_TANH ? DS2_RNN_LSTM : RNN;
-      // DS2_FWD_LL=0: grid barrier + TMA of h_{t-1} (round 1) instead of the flag-in-data exchange
-      int rc = env_flag("DS2_FWD_LL", 1) ? launch_fwd_splitk<R, true>(a, ws, ws_bytes, st)
+      // DS2_FWD_LL=1: flag-in-data exchange instead of grid barrier + TMA of h_{t-1}.  Measured SLOWER (13.9k vs 8.7k
+      // cycles per step, profiles/r02_ll_exchange.md): strong per-thread loads do not pipeline (~600 cycles each),
+      // and even with the TMA engine as transport the exchange costs what the barrier costs — the floor is the
+      // store -> L2 -> load visibility latency, not the barrier.  Kept as a tested, selectable variant.
+      int rc = env_flag("DS2_FWD_LL", 0) ? launch_fwd_splitk<R, true>(a, ws, ws_bytes, st)
                                          : launch_fwd_splitk<R, false>(a, ws, ws_bytes, st);
       if (rc != 1) return rc;
     }
@@ -2255,8 +2258,9 @@ static int launch_bwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
   const int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
   const int GH = G * a.H;
   if (!getenv("DS2_NO_RESIDENT")) {
-    // DS2_BWD_LL=0: grid barrier + TMA of dGh[t_next] (round 1) instead of the flag-in-data exchange
-    int rc = env_flag("DS2_BWD_LL", 1) ? launch_bwd_splitk_resident<RNN, CL, true>(a, ws, ws_bytes, st)
+    // DS2_BWD_LL=1: flag-in-data exchange instead of grid barrier + TMA of dGh[t_next] (measured slower, see the
+    // forward launcher)
+    int rc = env_flag("DS2_BWD_LL", 0) ? launch_bwd_splitk_resident<RNN, CL, true>(a, ws, ws_bytes, st)
                                        : launch_bwd_splitk_resident<RNN, CL, false>(a, ws, ws_bytes, st);
     if (rc != 1) return rc;
   }

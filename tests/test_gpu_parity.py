@@ -341,15 +341,15 @@ def _one_layer(rnn, T, B, In, H, seed):
 
 @pytest.mark.parametrize("rnn,B", [("lstm", 32), ("lstm", 20), ("gru", 20), ("lstm", 40), ("gru", 48)])
 def test_tf32_sweep_variants_agree_with_the_fp32_path(rnn, B, monkeypatch):
-    """forward: 2-CTA split-K clusters vs 16-unit CTAs; backward: 8- vs 4-CTA clusters (LSTM, B = 32); flag-in-data
-    exchange (default) vs grid barrier + TMA (DS2_FWD_LL / DS2_BWD_LL = 0); stores deferred past the barrier or not.  H = 256 takes every variant; B = 20 exercises the N padding (24 / 32 columns),
+    """forward: 2-CTA split-K clusters vs 16-unit CTAs; backward: 8- vs 4-CTA clusters (LSTM, B = 32); grid barrier + TMA
+    (default) vs the flag-in-data exchange (DS2_FWD_LL / DS2_BWD_LL = 1); stores deferred past the barrier or not.  H = 256 takes every variant; B = 20 exercises the N padding (24 / 32 columns),
     B > 32 the second pass of the epilogues over the batch columns."""
     run = _one_layer(rnn, T=33, B=B, In=192, H=256, seed=11)
     ds.set_precision("fp32")
     ref = run()
     ds.set_precision("tf32")
     variants = [{}, {"DS2_FWD_SPLITK": "0"}, {"DS2_SPLITK_CL": "4"}, {"DS2_SWEEP_DEFER": "0"},
-                {"DS2_FWD_LL": "0"}, {"DS2_BWD_LL": "0"}, {"DS2_FWD_LL": "0", "DS2_BWD_LL": "0", "DS2_SPLITK_CL": "4"},
+                {"DS2_FWD_LL": "1"}, {"DS2_BWD_LL": "1"}, {"DS2_FWD_LL": "1", "DS2_BWD_LL": "1", "DS2_SPLITK_CL": "4"},
                 {"DS2_FWD_SPLITK": "0", "DS2_SPLITK_CL": "4", "DS2_SWEEP_DEFER": "0"}]
     for env in variants:
         for k_, v in env.items():
@@ -415,9 +415,10 @@ def test_direct_gradient_sinks_equal_autograd_accumulation(rnn_type, bidir):
             snaps.append(flat.grad.clone())
         grads[direct] = snaps
         del model, flat
+    # (not bit-equal: the fp32-mode column sums / BatchNorm reductions use float atomics, whose order varies run to run)
     for a, b in zip(grads[False], grads[True]):
-        assert torch.equal(a, b)
-    assert not torch.equal(grads[True][0], grads[True][1])
+        assert rel(a, b) < 1e-5 and rel_l2(a, b) < 1e-6
+    assert rel(grads[True][0], grads[True][1]) > 1e-2          # the second step really overwrote the first
     model = make_model(rnn_type, bidir, 32, 2, ctx=5, params=P).train()       # no FlatParams: plain autograd grads
     x, targets, pct, tsz = batches[0]
     model.training_step((x.cuda(), targets, pct.clone(), tsz), 0).backward()
