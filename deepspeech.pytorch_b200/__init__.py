@@ -10,13 +10,15 @@ from .labels import LABELS
 
 
 def set_precision(name: str):
-    """'fp32' (FFMA everywhere) or 'tf32' (tcgen05 tensor cores for the dense GEMMs)."""
-    code = {"fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32}[name]
+    """'fp32' (FFMA everywhere), 'tf32' (tcgen05 tensor cores, TF32 operands for the dense GEMMs) or 'fp16' (the
+    reference's `precision: 16`: fp16 operand copies for the recurrent stack's GEMMs, everything else as 'tf32').
+    A `DeepSpeech(precision=16)` model selects 'fp16' by itself for its own calls."""
+    code = {"fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32, "fp16": _lib.PREC_F16}[name]
     _lib.check(get_lib().ds2_set_precision(code), "ds2_set_precision")
 
 
 def get_precision() -> str:
-    return {_lib.PREC_FP32: "fp32", _lib.PREC_TF32: "tf32"}[get_lib().ds2_get_precision()]
+    return {_lib.PREC_FP32: "fp32", _lib.PREC_TF32: "tf32", _lib.PREC_F16: "fp16"}[get_lib().ds2_get_precision()]
 
 
 from . import ops  # noqa: E402

@@ -98,7 +98,7 @@ int ds2_device_check(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 int ds2_set_precision(int prec) {
-  DS2_REQUIRE(prec == DS2_PREC_FP32 || prec == DS2_PREC_TF32, "unknown precision %d", prec);
+  DS2_REQUIRE(prec == DS2_PREC_FP32 || prec == DS2_PREC_TF32 || prec == DS2_PREC_F16, "unknown precision %d", prec);
   ds2::g_prec.store(prec);
   return DS2_OK;
 }

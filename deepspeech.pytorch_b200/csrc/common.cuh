@@ -13,6 +13,8 @@ namespace ds2 {
 void set_error(const char* fmt, ...);
 extern std::atomic<long long> g_launches;
 int precision();
+inline bool tensor_core_mode() { return precision() != DS2_PREC_FP32; }   // TF32 or precision-16: tcgen05 kernels
+inline bool f16_gemm_mode() { return precision() == DS2_PREC_F16; }       // fp16 operands for the dense RNN GEMMs
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -113,6 +115,16 @@ int gemm_simt(int transA, int transB, int M, int N, int K, float alpha, const fl
 int gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
             int ldb, float beta, float* C, int ldc, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t gemm_tc_workspace_bytes(int transA, int transB, int M, int N, int K);
+// precision-16 GEMM: fp16 K-major operands, fp32 accumulation / output (gemm_tc.cu); 1 = not eligible
+int gemm_tc_f16(int M, int N, int K, float alpha, const void* A16, int lda, const void* B16, int ldb, float beta,
+                float* C, int ldc, const float* alpha_dev, cudaStream_t st);
+// fp32 -> fp16 operand copies (convert.cu)
+int f32_to_f16_rows(int rows, int cols, const float* in, size_t ld_in, void* out, size_t ld_out, const float* scale_dev,
+                    cudaStream_t st);
+int f32_to_f16_transpose(int rows, int cols, const float* in, size_t ld_in, void* out, size_t ld_out, void* outT,
+                         size_t ld_outT, const float* scale_dev, cudaStream_t st);
+int pow2_scale_for(int rows, int cols, const float* x, size_t ld, unsigned int* absmax_ws, float* scale, int top,
+                   cudaStream_t st);
 
 // BatchNorm over rows of a (rows, F) matrix (BatchNorm1d under SequenceWise, model.py:18-33,86,196)
 // training: batch stats (biased var) -> mean/invstd, running stats updated; else running stats.

@@ -506,7 +506,7 @@ int ds2_conv_frontend_fwd(int B, int T, const float* x, const int32_t* out_len, 
   DS2_LAUNCH(bn2d_finalize_kernel, 1, 32, 0, st, (double)B * D1 * Tp, W.sums, g1, be1, rm1, rv1, training, momentum,
              eps, stats);
   DS2_LAUNCH(bn_act_kernel, 148 * 8, 256, 0, st, B, D1, Tp, z1, stats, g1, be1, out_len, a1);
-  if (precision() == DS2_PREC_TF32 && !getenv("DS2_NO_CONV_TC") && !getenv("DS2_NO_CONV_TC_FWD")) {
+  if (tensor_core_mode() && !getenv("DS2_NO_CONV_TC") && !getenv("DS2_NO_CONV_TC_FWD")) {
     // conv2 on tcgen05: channels-last copy of a1, packed taps, implicit GEMM with the kw taps folded into N
     rc = nchw_to_cl(B, D1, Tp, a1, W.cl, st);
     if (rc) return rc;
@@ -556,7 +556,7 @@ int ds2_conv_frontend_bwd(int B, int T, const float* x, const int32_t* out_len, 
   // ---- conv2 gradients
   {
     int wrc = 1;
-    if (precision() == DS2_PREC_TF32 && !getenv("DS2_NO_CONV_TC") && !getenv("DS2_NO_CONV_TC_WGRAD")) {
+    if (tensor_core_mode() && !getenv("DS2_NO_CONV_TC") && !getenv("DS2_NO_CONV_TC_WGRAD")) {
       wrc = conv2_wgrad_tc(W.du2, a1, W.shifted, B, Tp, dw2, st);
       if (wrc < 0) return wrc;
     }
@@ -567,7 +567,7 @@ int ds2_conv_frontend_bwd(int B, int T, const float* x, const int32_t* out_len, 
   // even rows y=2j (41 rows), odd rows y=2j+1 (40 rows) of d(a1) (B,32,81,T')
   const size_t ob = (size_t)CO * D1 * Tp, oc = (size_t)D1 * Tp;
   int rc;
-  if (precision() == DS2_PREC_TF32 && !getenv("DS2_NO_CONV_TC") && !getenv("DS2_NO_CONV_TC_DGRAD")) {
+  if (tensor_core_mode() && !getenv("DS2_NO_CONV_TC") && !getenv("DS2_NO_CONV_TC_DGRAD")) {
     // data gradient on tcgen05: rows y=2i use taps kh=2m (d = i+5-m), rows y=2i+1 taps kh=2m+1
     rc = nchw_to_cl(B, D2, Tp, W.du2, W.cl, st);
     if (rc) return rc;

@@ -143,7 +143,7 @@ int ds2_gemm(int transA, int transB, int M, int N, int K, float alpha, const flo
              int ldb, float beta, float* C, int ldc, void* ws, size_t ws_bytes, void* stream) {
   DS2_REQUIRE(M >= 0 && N >= 0 && K >= 0 && A && B && C, "ds2_gemm: bad arguments");
   cudaStream_t st = ds2::as_stream(stream);
-  if (ds2::precision() == DS2_PREC_TF32) {
+  if (ds2::tensor_core_mode()) {
     int r = ds2::gemm_tc(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, ws, ws_bytes, st);
     if (r <= 0) return r;  // 0 = done, <0 = error, 1 = shape not eligible -> FFMA kernel
   }

@@ -189,13 +189,21 @@ __device__ __forceinline__ uint64_t smem_desc_mn(uint32_t smem_addr, uint32_t la
 
 // gridDim.z > 1: split-K, every CTA adds its partial tile into C with vector atomics (C holds beta * C_old,
 // prepared by the host).
-template <bool A_MN, bool B_MN, int NMB, int STG>
+// F16 (both operands K-major fp16 in memory, precision-16 mode): the 128-byte swizzle rows hold 64 halfs instead of
+// 32 floats, so a stage covers twice the K extent with the same bytes, the same four 32-byte k-steps per stage and
+// tcgen05.mma.kind::f16 (K = 16) at twice the tensor rate; accumulation and C stay fp32.  `alpha_dev` (optional)
+// multiplies alpha by a device-resident factor (the inverse of the power-of-two scale of a scaled fp16 operand).
+template <bool A_MN, bool B_MN, int NMB, int STG, bool F16 = false>
 __global__ void __launch_bounds__(gtc::THREADS, gtc::Cfg<NMB, STG>::CTAS_PER_SM)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-               float alpha, float beta, float* __restrict__ C, int ldc, unsigned int mn_cfg, int mn3d) {
+               float alpha, float beta, float* __restrict__ C, int ldc, unsigned int mn_cfg, int mn3d,
+               const float* __restrict__ alpha_dev) {
   using namespace gtc;
   using namespace tc;
   using G = Cfg<NMB, STG>;
+  static_assert(!F16 || (!A_MN && !B_MN), "fp16 operands are K-major only");
+  constexpr int BK = F16 ? 2 * gtc::BK : gtc::BK;         // K elements per stage (shadows gtc::BK)
+  if (alpha_dev) alpha *= __ldg(alpha_dev);
   constexpr int BM = G::BM, STAGES = G::STAGES, STAGE_BYTES = G::STAGE_BYTES, A_BYTES = G::A_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -254,7 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = instr_desc(FMT_TF32, 128, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+      constexpr uint32_t idesc = instr_desc(F16 ? FMT_F16 : FMT_TF32, 128, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
       const uint32_t mn_layout = mn_cfg & 7u, lbo = ((mn_cfg >> 4) & 0x3FFFu) << 4, sbo = (mn_cfg >> 18) << 4;
       for (int it = 0; it < nk; ++it) {
         const int s = it % STAGES;
@@ -270,9 +278,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int mb = 0; mb < NMB; ++mb) {
           // M block mb: rows 128*mb.. of the A tile are 16 KB further in either layout; its accumulator 256 columns
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k)
-            mma_tf32(tmem_base + (uint32_t)(mb * 256), adesc + (uint64_t)(mb * 1024) + (uint64_t)k * a_adv,
-                     bdesc + (uint64_t)k * b_adv, idesc, (it | k) != 0);
+          for (int k = 0; k < 4; ++k) {                  // four 32-byte k-steps per 128-byte row (K = 8 tf32 / 16 fp16)
+            if (F16)
+              mma_f16(tmem_base + (uint32_t)(mb * 256), adesc + (uint64_t)(mb * 1024) + (uint64_t)k * a_adv,
+                      bdesc + (uint64_t)k * b_adv, idesc, (it | k) != 0);
+            else
+              mma_tf32(tmem_base + (uint32_t)(mb * 256), adesc + (uint64_t)(mb * 1024) + (uint64_t)k * a_adv,
+                       bdesc + (uint64_t)k * b_adv, idesc, (it | k) != 0);
+          }
         }
         mma_commit(&empty[s]);             // stage reusable when these MMAs have read it
       }
@@ -538,11 +551,11 @@ size_t gemm_tc_workspace_bytes(int transA, int transB, int M, int N, int K) {
 
 static bool tc_eligible(int M, int N, int K) { return K >= 32 && M >= 32 && N >= 16 && (long long)M * N * K >= (1 << 18); }
 
-template <bool A_MN, bool B_MN, int NMB, int STG>
+template <bool A_MN, bool B_MN, int NMB, int STG, bool F16 = false>
 static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, float alpha, float beta,
-                          float* C, int ldc, int mn3d, int splits, cudaStream_t st) {
+                          float* C, int ldc, int mn3d, int splits, cudaStream_t st, const float* alpha_dev = nullptr) {
   using G = gtc::Cfg<NMB, STG>;
-  auto kern = gemm_tc_kernel<A_MN, B_MN, NMB, STG>;
+  auto kern = gemm_tc_kernel<A_MN, B_MN, NMB, STG, F16>;
   static DeviceOnce attr_once;
   if (attr_once.first()) {
     DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
@@ -553,7 +566,7 @@ static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M,
   if (splits > 1 && beta == 0.f)
     DS2_CHECK_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
   dim3 grid(cdiv(N, gtc::BN), cdiv(M, G::BM), splits);
-  DS2_LAUNCH(kern, grid, gtc::THREADS, G::SMEM_BYTES, st, tmA, tmB, M, N, K, alpha, beta, C, ldc, mn_cfg, mn3d);
+  DS2_LAUNCH(kern, grid, gtc::THREADS, G::SMEM_BYTES, st, tmA, tmB, M, N, K, alpha, beta, C, ldc, mn_cfg, mn3d, alpha_dev);
   return DS2_OK;
 }
 
@@ -671,6 +684,28 @@ int gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const floa
   if (b_mn) { DS2_GEMM_DISPATCH(false, true); }
   DS2_GEMM_DISPATCH(false, false);
 #undef DS2_GEMM_DISPATCH
+}
+
+// C[M,N] (fp32) = alpha * [*alpha_dev] * A[M,K] . B[N,K]^T + beta * C with fp16 K-major operands (precision-16 mode).
+// Returns 1 when the shape / alignment is not eligible (the caller then runs the TF32 path on the fp32 tensors).
+int gemm_tc_f16(int M, int N, int K, float alpha, const void* A16, int lda, const void* B16, int ldb, float beta,
+                float* C, int ldc, const float* alpha_dev, cudaStream_t st) {
+  if (!tc_eligible(M, N, K) || M < 128) return 1;
+  if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A16) & 15) || (reinterpret_cast<uintptr_t>(B16) & 15)) return 1;
+  int cfg = 1, splits = 1;
+  const long long tiles2 = (long long)cdiv(M, 256) * cdiv(N, gtc::BN);
+  if (M >= 256) {
+    if (tiles2 >= 90) cfg = 2;
+    else if (tiles2 * 2 >= 100 && tiles2 * 2 <= 148 && K >= 4096 && (beta == 0.f || beta == 1.f)) { cfg = 2; splits = 2; }
+  }
+  const int bm = cfg == 2 ? 256 : 128;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_f16(&tmA, A16, 2, K, M, 1, (size_t)lda, 0, 64, bm, 1);
+  if (rc) return rc;
+  rc = make_tmap_f16(&tmB, B16, 2, K, N, 1, (size_t)ldb, 0, 64, gtc::BN, 1);
+  if (rc) return rc;
+  if (cfg == 2) return launch_gemm_tc<false, false, 2, 3, true>(tmA, tmB, M, N, K, alpha, beta, C, ldc, 0, splits, st, alpha_dev);
+  return launch_gemm_tc<false, false, 1, 4, true>(tmA, tmB, M, N, K, alpha, beta, C, ldc, 0, splits, st, alpha_dev);
 }
 
 }  // namespace ds2

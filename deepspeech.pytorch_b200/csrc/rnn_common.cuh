@@ -24,6 +24,15 @@ struct SeqArgs {
   float* dbias[2];
   float* dbias_hn[2];
   int* dbias_done;
+  // bwd, optional (precision-16 GEMM operands): fp16 copies of the gate gradients, multiplied by the power of two
+  // f16_scale[0] (device), written by the sweep as it produces them — f16_dg (T*B, D*G*H) row-major, f16_dgT
+  // (D*G*H, T*B) transposed, f16_auxT (D*H, T*B) GRU h-side n-gate gradient transposed.  The sweep sets
+  // *f16_done = 1 when it filled them (otherwise the caller converts from the fp32 gate gradients).
+  void* f16_dg;
+  void* f16_dgT;
+  void* f16_auxT;
+  const float* f16_scale;
+  int* f16_done;
 };
 
 }  // namespace ds2

@@ -9,6 +9,8 @@
 //
 // reserve layout (floats):  gates (T,B,D,G*H) | hseq (D,T,B,H) | aux (D,T,B,H: LSTM cell states /
 //                           GRU W_hn h + b_hn; absent for tanh) | bn mean,invstd (2*In)
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "rnn_cells.cuh"
 #include "rnn_common.cuh"
@@ -285,6 +287,11 @@ size_t ds2_rnn_workspace_bytes(const ds2_rnn_desc* d) {
   n += align_up(2 * (size_t)d->In * 8, 256);              // BN double sums
   n += D * align_up(GH * d->H * 4, 256);                  // W_hh^T per direction
   n += align_up(D * (size_t)d->B * d->H * 4, 256);        // carry
+  if (f16_gemm_mode()) {
+    // precision-16 operand copies: x16, W16 (fwd); dG16, dG16^T, x16^T, h16^T, aux16^T, W16^T, scale (bwd)
+    n += 2 * align_up(TB * d->In * 2, 256) + 2 * align_up(D * GH * d->In * 2, 256) + 2 * align_up(TB * D * GH * 2, 256) +
+         2 * align_up(D * d->H * TB * 2, 256) + 512;
+  }
   n += rnn_sweep_tc_workspace_bytes(d->rnn_type, d->T, d->B, d->H, (int)D);
   n += ds2_gemm_workspace_bytes(1, 0, (int)GH, d->In > d->H ? d->In : d->H, (int)TB);
   return n + 4096;
@@ -325,7 +332,26 @@ int ds2_rnn_layer_fwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
   // input projection for every time step and both directions: gates[:, d*GH:(d+1)*GH] = xin . W_ih[d]^T
   {
     DS2_PROF("rnn_fwd_proj_gemm", st);
-    for (int dir = 0; dir < D; ++dir) {
+    bool done = false;
+    if (f16_gemm_mode() && B % 8 == 0 && In % 8 == 0 && H % 8 == 0) {
+      // precision 16: fp16 copies of the layer input and of both directions' W_ih (stacked: one N = D*G*H GEMM)
+      __half* x16 = ar.take<__half>((size_t)TB * In);
+      __half* w16 = ar.take<__half>((size_t)D * GH * In);
+      if (x16 && w16) {
+        rc = f32_to_f16_rows(TB, In, xin, In, x16, In, nullptr, st);
+        if (rc) return rc;
+        for (int dir = 0; dir < D; ++dir) {
+          rc = f32_to_f16_rows(GH, In, w_ih[dir], In, w16 + (size_t)dir * GH * In, In, nullptr, st);
+          if (rc) return rc;
+        }
+        rc = gemm_tc_f16(TB, D * GH, In, 1.f, x16, In, w16, In, 0.f, R.gates, D * GH, nullptr, st);
+        if (rc < 0) return rc;
+        done = rc == 0;
+      }
+      gws = ar.base + ar.off;
+      gws_bytes = ar.cap - ar.off;
+    }
+    for (int dir = 0; dir < D && !done; ++dir) {
       rc = ds2_gemm(0, 1, TB, GH, In, 1.f, xin, In, w_ih[dir], In, 0.f, R.gates + (size_t)dir * GH, D * GH, gws,
                     gws_bytes, stream);
       if (rc) return rc;
@@ -339,7 +365,7 @@ int ds2_rnn_layer_fwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
   {
     DS2_PROF("rnn_fwd_sweep", st);
     rc = 1;
-    if (precision() == DS2_PREC_TF32) {
+    if (tensor_core_mode()) {
       rc = rnn_sweep_fwd_tc(d->rnn_type, a, gws, gws_bytes, st);
       if (rc == 1) note_fallback("forward sweep", d->rnn_type, T, B, H, D);
     }
@@ -403,10 +429,37 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
     if (gru_l) DS2_CHECK_CUDA(cudaMemsetAsync(db_hh[dir] + 2 * H, 0, sizeof(float) * H, st));
   }
   a.dbias_done = &dbias_done;
+  // ---- precision 16: scaled fp16 copies of the gate gradients (row-major for dX, transposed for the weight
+  // gradients), transposed fp16 copies of the layer input / the hidden sequence / W_ih; every GEMM K-major fp16.
+  // The split-K sweep writes the gate-gradient copies itself (scale from max|dY|); other sweeps leave f16_done = 0
+  // and the copies are converted from the fp32 gate gradients afterwards.
+  const bool gru = d->rnn_type == DS2_RNN_GRU;
+  __half *dG16 = nullptr, *dG16T = nullptr, *x16T = nullptr, *h16T = nullptr, *aux16T = nullptr, *w16T = nullptr;
+  float* scale = nullptr;
+  int f16_done = 0;
+  bool f16 = f16_gemm_mode() && B % 8 == 0 && In % 8 == 0 && H % 8 == 0 && TB >= 128;
+  if (f16) {
+    const size_t DGH = (size_t)D * GH;
+    dG16 = ar.take<__half>((size_t)TB * DGH);
+    dG16T = ar.take<__half>((size_t)TB * DGH);
+    x16T = ar.take<__half>((size_t)TB * In);
+    h16T = ar.take<__half>((size_t)D * H * TB);
+    aux16T = gru ? ar.take<__half>((size_t)D * H * TB) : nullptr;
+    w16T = ar.take<__half>((size_t)In * DGH);
+    scale = ar.take<float>(16);
+    f16 = dG16 && dG16T && x16T && h16T && w16T && scale && (!gru || aux16T);
+    gws = ar.base + ar.off;
+    gws_bytes = ar.cap - ar.off;
+  }
+  if (f16) {
+    rc = pow2_scale_for(TB, H, dy, (size_t)H, reinterpret_cast<unsigned int*>(scale + 8), scale, 5, st);
+    if (rc) return rc;
+    a.f16_dg = dG16; a.f16_dgT = dG16T; a.f16_auxT = aux16T; a.f16_scale = scale; a.f16_done = &f16_done;
+  }
   {
     DS2_PROF("rnn_bwd_sweep", st);
     rc = 1;
-    if (precision() == DS2_PREC_TF32) {
+    if (tensor_core_mode()) {
       rc = rnn_sweep_bwd_tc(d->rnn_type, a, gws, gws_bytes, st);
       if (rc == 1) note_fallback("backward sweep", d->rnn_type, T, B, H, D);
     }
@@ -422,15 +475,49 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
     if (rc) return rc;
     xin = xbn;
   }
-  const bool gru = d->rnn_type == DS2_RNN_GRU;
   DS2_PROF("rnn_bwd_gemms", st);
+  if (f16) {
+    const size_t DGH = (size_t)D * GH;
+    if (!f16_done) {
+      unsigned int* absmax_ws = reinterpret_cast<unsigned int*>(scale + 8);
+      rc = pow2_scale_for(TB, (int)DGH, R.gates, DGH, absmax_ws, scale, 10, st);
+      if (rc) return rc;
+      rc = f32_to_f16_transpose(TB, (int)DGH, R.gates, DGH, dG16, DGH, dG16T, (size_t)TB, scale, st);
+      if (rc) return rc;
+    }
+    rc = f32_to_f16_transpose(TB, In, xin, (size_t)In, nullptr, 0, x16T, (size_t)TB, nullptr, st);
+    if (rc) return rc;
+    for (int dir = 0; dir < D; ++dir) {
+      rc = f32_to_f16_transpose(TB, H, R.hseq + (size_t)dir * TB * H, (size_t)H, nullptr, 0, h16T + (size_t)dir * H * TB,
+                                (size_t)TB, nullptr, st);
+      if (rc) return rc;
+      if (gru && !f16_done) {
+        rc = f32_to_f16_transpose(TB, H, R.aux + (size_t)dir * TB * H, (size_t)H, nullptr, 0,
+                                  aux16T + (size_t)dir * H * TB, (size_t)TB, scale, st);
+        if (rc) return rc;
+      }
+      rc = f32_to_f16_transpose(GH, In, w_ih[dir], (size_t)In, nullptr, 0, w16T + (size_t)dir * GH, DGH, nullptr, st);
+      if (rc) return rc;
+    }
+  }
+  bool dx_done = false;
+  if (f16 && dx) {   // dX = dG (TB x D*GH) . [W_ih fwd ; W_ih rev] : one K = D*G*H GEMM for both directions
+    rc = gemm_tc_f16(TB, In, D * GH, 1.f, dG16, D * GH, w16T, D * GH, 0.f, bn_gamma ? dxbn : dx, In, scale + 1, st);
+    if (rc < 0) return rc;
+    dx_done = rc == 0;
+  }
   for (int dir = 0; dir < D; ++dir) {
     const float* dG = R.gates + (size_t)dir * GH;   // (TB, GH) with row stride D*GH : dGx
     const int ldg = D * GH;
     const float* aux_d = R.aux ? R.aux + (size_t)dir * TB * H : nullptr;   // GRU: dGh_n (TB,H)
     const float* hseq_d = R.hseq + (size_t)dir * TB * H;
     // dW_ih = dGx^T . xin
-    rc = ds2_gemm(1, 0, GH, In, TB, 1.f, dG, ldg, xin, In, 0.f, dw_ih[dir], In, gws, gws_bytes, stream);
+    rc = 1;
+    if (f16) {
+      rc = gemm_tc_f16(GH, In, TB, 1.f, dG16T + (size_t)dir * GH * TB, TB, x16T, TB, 0.f, dw_ih[dir], In, scale + 1, st);
+      if (rc < 0) return rc;
+    }
+    if (rc == 1) rc = ds2_gemm(1, 0, GH, In, TB, 1.f, dG, ldg, xin, In, 0.f, dw_ih[dir], In, gws, gws_bytes, stream);
     if (rc) return rc;
     if (!dbias_done) {
       rc = colsum(TB, GH, dG, ldg, db_ih[dir], st);
@@ -441,12 +528,26 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
     const size_t a_off = dir == 0 ? (size_t)B : 0, h_off = dir == 0 ? 0 : (size_t)B;
     const int rows_x = gru ? 2 * H : GH;   // rows whose dGh == dGx
     if (Kr > 0) {
-      rc = ds2_gemm(1, 0, rows_x, H, Kr, 1.f, dG + a_off * ldg, ldg, hseq_d + h_off * H, H, 0.f, dw_hh[dir], H, gws,
-                    gws_bytes, stream);
+      rc = 1;
+      if (f16) {   // in the transposed copies a shift by one time step is a shift by B columns
+        rc = gemm_tc_f16(rows_x, H, Kr, 1.f, dG16T + (size_t)dir * GH * TB + a_off, TB, h16T + (size_t)dir * H * TB + h_off,
+                         TB, 0.f, dw_hh[dir], H, scale + 1, st);
+        if (rc < 0) return rc;
+      }
+      if (rc == 1)
+        rc = ds2_gemm(1, 0, rows_x, H, Kr, 1.f, dG + a_off * ldg, ldg, hseq_d + h_off * H, H, 0.f, dw_hh[dir], H, gws,
+                      gws_bytes, stream);
       if (rc) return rc;
       if (gru) {
-        rc = ds2_gemm(1, 0, H, H, Kr, 1.f, aux_d + a_off * H, H, hseq_d + h_off * H, H, 0.f,
-                      dw_hh[dir] + (size_t)2 * H * H, H, gws, gws_bytes, stream);
+        rc = 1;
+        if (f16) {
+          rc = gemm_tc_f16(H, H, Kr, 1.f, aux16T + (size_t)dir * H * TB + a_off, TB, h16T + (size_t)dir * H * TB + h_off,
+                           TB, 0.f, dw_hh[dir] + (size_t)2 * H * H, H, scale + 1, st);
+          if (rc < 0) return rc;
+        }
+        if (rc == 1)
+          rc = ds2_gemm(1, 0, H, H, Kr, 1.f, aux_d + a_off * H, H, hseq_d + h_off * H, H, 0.f,
+                        dw_hh[dir] + (size_t)2 * H * H, H, gws, gws_bytes, stream);
         if (rc) return rc;
       }
     } else {
@@ -462,7 +563,7 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
       DS2_CHECK_CUDA(cudaMemcpyAsync(db_hh[dir], db_ih[dir], sizeof(float) * GH, cudaMemcpyDeviceToDevice, st));
     }
     // dX (pre-BN-affine) += dGx . W_ih
-    if (dx) {
+    if (dx && !dx_done) {
       rc = ds2_gemm(0, 0, TB, In, GH, 1.f, dG, ldg, w_ih[dir], In, dir == 0 ? 0.f : 1.f, bn_gamma ? dxbn : dx, In,
                     gws, gws_bytes, stream);
       if (rc) return rc;

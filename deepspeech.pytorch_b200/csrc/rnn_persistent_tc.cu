@@ -53,6 +53,10 @@ struct PersistParams {
   __half* dg16;         // resident bwd: scaled fp16 copy of dGh (T*B, D*G*H)
   unsigned int* gmax;   // resident bwd: [D][T+1] float bits of max|dGh| per processed step (slot 0: bound from dY)
   unsigned int* dymax;  // resident bwd: [T] float bits of max_b,u |dY[t]| (the scale of a step also covers its own dY)
+  __half* dgn16;        // resident bwd, optional: fp16 copy of the gate gradients x nscale, (T*B, D*G*H) row-major
+  __half* dgn16T;       //   ... transposed (D*G*H, T*B)
+  __half* auxn16T;      //   ... GRU h-side n-gate gradient, transposed (D*H, T*B)
+  const float* nscale;  //   device: power-of-two scale of those copies
   unsigned int* gmeta;  // LL bwd: [D][T][NT*CL*4] float bits of max|dGh| per (step, epilogue warp), 0xFFFFFFFF = not yet
   long long* trace;     // optional: clock64 stamps of CTA 0, 4 per step
   const int32_t* len;
@@ -1310,6 +1314,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
     float s_cur = pow2f(sx_cur), inv_prev = 1.f;
     const int cta_in_dir = ut * CL + ks, nmeta = NTc * CL * 4;
     (void)gmax_d;
+    const float nscale = (RES && p.dgn16) ? __ldg(p.nscale) : 1.f;
     for (int step = 0; step < T; ++step) {
       const int t = d == 0 ? T - 1 - step : step;
       const int tp = d == 0 ? t - 1 : t + 1;
@@ -1526,6 +1531,33 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
 #pragma unroll
         for (int g = 0; g < G; ++g) st4(gp + g * H, o[g]);
         if (RNN == DS2_RNN_GRU) st4(p.aux + (((size_t)d * T + t) * B + b) * H + u0 + uq, o[4]);
+        if (RES && p.dgn16) {
+          // precision-16 GEMM operands, produced where the values are: the row-major copy (dX) as 8-byte stores, the
+          // transposed copies (dW_ih, dW_hh: the reduction index t*B+b must be contiguous) as 2-byte stores — 8
+          // consecutive batch columns of a (gate, unit) come from 8 lanes of a warp and are merged in L2
+          const size_t TBs = (size_t)T * B, col = (size_t)t * B + b;
+          __half* r16 = p.dgn16 + (col * D + d) * GH + u0 + uq;
+          __half* t16 = p.dgn16T + ((size_t)d * GH + u0 + uq) * TBs + col;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            __half h[NPF];
+#pragma unroll
+            for (int j = 0; j < NPF; ++j) {
+              h[j] = to_half_sat(o[g][j] * nscale);
+              t16[((size_t)g * H + j) * TBs] = h[j];
+            }
+            const __half2 lo = __halves2half2(h[0], h[1]), hi = __halves2half2(h[2], h[3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const unsigned int*>(&lo);
+            pk.y = *reinterpret_cast<const unsigned int*>(&hi);
+            *reinterpret_cast<uint2*>(r16 + g * H) = pk;
+          }
+          if (RNN == DS2_RNN_GRU) {
+            __half* a16 = p.auxn16T + ((size_t)d * H + u0 + uq) * TBs + col;
+#pragma unroll
+            for (int j = 0; j < NPF; ++j) a16[(size_t)j * TBs] = to_half_sat(o[4][j] * nscale);
+          }
+        }
       };
       // LL: fetch the scaled fp16 gate gradients dGh[t] of ALL units of this CTA's K range (written by every CTA of
       // the direction) into the swizzled K-major tile of the next step's MMAs; same packet / group scheme as the
@@ -2170,6 +2202,12 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
   p.trace = trace_ptr_from_env("DS2_TRACE_BWD");
   p.defer = sweep_defer_default();
   for (int d = 0; d < a.D; ++d) { p.dbias[d] = a.dbias[d]; p.dbias_hn[d] = a.dbias_hn[d]; }
+  if (a.f16_dg && a.f16_dgT && a.f16_scale && (RNN != DS2_RNN_GRU || a.f16_auxT)) {
+    p.dgn16 = static_cast<__half*>(a.f16_dg);
+    p.dgn16T = static_cast<__half*>(a.f16_dgT);
+    p.auxn16T = static_cast<__half*>(a.f16_auxT);
+    p.nscale = a.f16_scale;
+  }
   set_acc_layout(p);
   char* base = static_cast<char*>(ws);
   p.err = reinterpret_cast<int*>(base);
@@ -2249,6 +2287,7 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
   }
   DS2_LAUNCH(sweep_check_kernel, 1, 1, 0, st, p.err);
   if (a.dbias_done && a.dbias[0]) *a.dbias_done = 1;
+  if (a.f16_done && p.dgn16) *a.f16_done = 1;
   return DS2_OK;
 }
 

@@ -123,8 +123,24 @@ class DeepSpeech(_Base):
 
     # ------------------------------------------------------------------ forward (model.py:214-239)
     def forward(self, x, lengths, hs: Optional[list] = None):
+        """model.py:214-239.  `precision == 16` (the reference wraps this call in autocast, model.py:255 /
+        inference.py:94, and Lightning does so for training) selects the library's precision-16 mode for the duration
+        of the call; the autograd nodes remember it for their backward.  Any other value leaves the process-wide
+        switch (`set_precision`) alone."""
         if not x.is_cuda:
             raise _lib.Ds2Error("DeepSpeech (B200 shell): input must be a CUDA tensor; there is no CPU path")
+        if self.precision == 16:
+            lib = _lib.get_lib()
+            saved = lib.ds2_get_precision()
+            if saved != _lib.PREC_F16:
+                lib.ds2_set_precision(_lib.PREC_F16)
+                try:
+                    return self._forward(x, lengths, hs)
+                finally:
+                    lib.ds2_set_precision(saved)
+        return self._forward(x, lengths, hs)
+
+    def _forward(self, x, lengths, hs: Optional[list] = None):
         lengths = torch.as_tensor(lengths).cpu().int()
         output_lengths = self.get_seq_lens(lengths)
         ol = output_lengths.tolist()

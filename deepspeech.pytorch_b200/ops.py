@@ -73,7 +73,21 @@ def _on_device(fn):
             raise _lib.Ds2Error(f"{fn.__qualname__}: no CUDA tensor among the arguments (the B200 path has no CPU "
                                 "fallback)")
         with torch.cuda.device(dev):
-            return fn(ctx, *args)
+            lib = get_lib()
+            if fn.__name__ == "forward":
+                ctx.ds2_prec = lib.ds2_get_precision()
+                return fn(ctx, *args)
+            # backward: same arithmetic mode as the forward that recorded the graph (the switch is process-global
+            # and a precision-16 model sets it only for the duration of its own forward)
+            cur = lib.ds2_get_precision()
+            want = getattr(ctx, "ds2_prec", cur)
+            if want == cur:
+                return fn(ctx, *args)
+            lib.ds2_set_precision(want)
+            try:
+                return fn(ctx, *args)
+            finally:
+                lib.ds2_set_precision(cur)
     return wrapped
 
 

@@ -22,6 +22,11 @@
  *            DS2_PREC_TF32 = dense GEMMs (input projections, recurrent products, weight gradients)
  *            on tcgen05 tensor cores with TF32 operands / fp32 accumulation — the same arithmetic
  *            class the reference's stock CUDA path uses (cuDNN allow_tf32=True).
+ *            DS2_PREC_F16 = the reference's `precision: 16` (configs/librispeech.yaml:12, torch autocast): the
+ *            dense GEMMs of the recurrent stack (input projections, weight gradients, data gradients) take fp16
+ *            operand copies (gradients scaled by a power of two per tensor), fp32 accumulation; the recurrent
+ *            products already use fp16 operands; conv front-end / fc head as in TF32 mode; parameters,
+ *            activations, gradients and the optimizer stay fp32 (what autocast keeps in fp32 too).
  */
 #ifndef DS2_B200_H_
 #define DS2_B200_H_
@@ -40,7 +45,7 @@ extern "C" {
 #define DS2_ERR_WORKSPACE     -4   /* workspace too small                                         */
 
 enum { DS2_RNN_LSTM = 0, DS2_RNN_GRU = 1, DS2_RNN_TANH = 2 };   /* reference enums.py:18-21 */
-enum { DS2_PREC_FP32 = 0, DS2_PREC_TF32 = 1 };
+enum { DS2_PREC_FP32 = 0, DS2_PREC_TF32 = 1, DS2_PREC_F16 = 2 };
 
 /* Fixed geometry of the reference front-end (model.py:157-164). */
 #define DS2_NUM_FREQ   161

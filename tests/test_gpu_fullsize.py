@@ -107,9 +107,13 @@ FULL_CASES = [
 ]
 
 
+@pytest.mark.parametrize("prec", ["tf32", "fp16"])
 @pytest.mark.parametrize("tag,rnn,bidir,T,B,In,H", FULL_CASES)
-def test_full_size_layer_forward_and_backward_vs_fp32_reference(tag, rnn, bidir, T, B, In, H):
-    ds.set_precision("tf32")
+def test_full_size_layer_forward_and_backward_vs_fp32_reference(tag, rnn, bidir, T, B, In, H, prec):
+    """prec = "fp16": the precision-16 mode (fp16 operand copies for the projection / weight-gradient / data-gradient
+    GEMMs, gradients scaled by a power of two per tensor) — same bounds: fp16 carries TF32's 10-bit mantissa."""
+    ds.set_precision(prec)
+    tag = f"{tag}[{prec}]"
     ds.get_lib().ds2_fallback_count(1)
     x, lens, P, dy = _layer_case(rnn, bidir, T, B, In, H, seed=17)
     got = _run_b200(rnn, bidir, x, lens, P, dy)
@@ -198,3 +202,42 @@ def test_full_model_tf32_logits_within_north_star_bound():
     print(f"\n[fullsize] 5x bi-LSTM-1024 logits vs fp32 reference: B200 path rel {m:.2e} rel-L2 {l2:.2e}; "
           f"reference's default cuDNN-TF32 path rel {ms:.2e} rel-L2 {l2s:.2e}", flush=True)
     assert m < 1.5e-3 and m < max(1e-3, 2.0 * ms), (m, l2, ms, l2s)
+
+
+def test_precision_16_model_selects_fp16_mode_and_matches_reference():
+    """`DeepSpeech(precision=16)` (the reference's shipped configs) runs the library's precision-16 mode for its own
+    forward / backward regardless of the process-wide switch, and restores the switch afterwards.  Compared with the
+    fp32 reference arithmetic on a 3-layer bi-GRU-256 (GRU exercises the separate h-side n-gate gradient copy)."""
+    from gpu_helpers import oracle_cfg
+    import deepspeech_pytorch_b200 as dsm
+    ds.set_precision("tf32")
+    ocfg = oracle_cfg("gru", True, 256, 3)
+    P = O.init_params(ocfg, seed=21)
+    B, T = 8, 240
+    x, targets, pct, tsz = O.synth_batch(B, T, seed=6, lmin=20, lmax=40)
+    cfg = dsm.BiDirectionalConfig(rnn_type=dsm.RNNType.gru, hidden_size=256, hidden_layers=3)
+    model = dsm.DeepSpeech(dsm.LABELS, cfg, 16, dsm.AdamConfig(), dsm.SpectConfig())
+    model.load_state_dict(P)
+    model = model.cuda().train()
+    loss = model.training_step((x.cuda(), targets, pct.clone(), tsz), 0)
+    assert ds.get_precision() == "tf32"                      # restored after the forward
+    loss.backward()                                          # the nodes re-establish fp16 mode for their backward
+    assert ds.get_precision() == "tf32"
+    Pc = {k: (v.cuda().requires_grad_(True) if v.dtype.is_floating_point and "running_" not in k else v.cuda())
+          for k, v in P.items()}
+    import torch.nn.functional as F
+    with _fp32_reference_arithmetic():
+        sizes = O.input_sizes_from_percentages(pct.clone(), T)
+        out, osz, _, _ = O.forward(x.cuda(), sizes, Pc, ocfg, training=True, use_aten_rnn=True)
+        ref = F.ctc_loss(out.transpose(0, 1).double().log_softmax(-1), targets, osz, tsz, blank=0, reduction="sum",
+                         zero_infinity=True)
+        ref.backward()
+    assert abs(float(loss) - float(ref)) <= 2e-3 * max(1.0, abs(float(ref)))
+    worst = 0.0
+    for k, p in model.named_parameters():
+        e = rel_l2(p.grad, Pc[k].grad)
+        worst = max(worst, e)
+        assert e < 3e-2, (k, e)
+        assert torch.isfinite(p.grad).all()
+    print(f"\n[fullsize] precision=16 bi-GRU-256x3: loss rel {abs(float(loss) - float(ref)) / abs(float(ref)):.2e}, "
+          f"worst gradient rel-L2 {worst:.2e}", flush=True)
