@@ -16,7 +16,7 @@ vp, i32, i64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 
 class RnnDesc(C.Structure):
     _fields_ = [("rnn_type", i32), ("bidirectional", i32), ("T", i32), ("B", i32), ("In", i32), ("H", i32),
-                ("training", i32), ("bn_momentum", f32), ("bn_eps", f32)]
+                ("training", i32), ("bn_momentum", f32), ("bn_eps", f32), ("deferred_dw", i32)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/ds2_b200.h (tests check this)
@@ -28,6 +28,8 @@ PROTOTYPES = {
     "ds2_get_precision": (i32, []),
     "ds2_launch_count": (i64, [i32]),
     "ds2_fallback_count": (i64, [i32]),
+    "ds2_set_side_stream": (i32, [vp]),
+    "ds2_join_side_stream": (i32, [vp]),
     "ds2_prof_enable": (i32, [i32]),
     "ds2_prof_report": (i32, [C.c_char_p, sz]),
     "ds2_seq_lens_host": (i32, [vp, i32, vp]),

@@ -32,6 +32,36 @@ int device_sm_count() {
   return v;
 }
 
+std::atomic<void*> g_side_stream{nullptr};
+std::mutex g_side_mu;
+cudaEvent_t g_join_event = nullptr;
+static std::map<const void*, cudaEvent_t> g_ws_events;   // workspace base -> "side work reading it has finished"
+
+// main: order `main` after the side work that last used workspace `ws` (before the workspace is overwritten)
+int side_wait_for_workspace(const void* ws, cudaStream_t main) {
+  std::lock_guard<std::mutex> lk(g_side_mu);
+  auto it = g_ws_events.find(ws);
+  if (it != g_ws_events.end()) DS2_CHECK_CUDA(cudaStreamWaitEvent(main, it->second, 0));
+  return DS2_OK;
+}
+// fork: the side stream starts after everything queued on `main` so far
+int side_fork(cudaStream_t main, cudaStream_t side) {
+  std::lock_guard<std::mutex> lk(g_side_mu);
+  static cudaEvent_t fork_ev = nullptr;
+  if (!fork_ev) DS2_CHECK_CUDA(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+  DS2_CHECK_CUDA(cudaEventRecord(fork_ev, main));
+  DS2_CHECK_CUDA(cudaStreamWaitEvent(side, fork_ev, 0));
+  return DS2_OK;
+}
+// the side work queued so far is the last reader of workspace `ws`
+int side_mark_workspace(const void* ws, cudaStream_t side) {
+  std::lock_guard<std::mutex> lk(g_side_mu);
+  cudaEvent_t& ev = g_ws_events[ws];
+  if (!ev) DS2_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  DS2_CHECK_CUDA(cudaEventRecord(ev, side));
+  return DS2_OK;
+}
+
 std::atomic<long long> g_fallbacks{0};
 void note_fallback(const char* what, int rnn, int T, int B, int H, int D) {
   static std::mutex mu;
@@ -107,6 +137,25 @@ int ds2_get_precision(void) { return ds2::precision(); }
 int64_t ds2_launch_count(int reset) {
   long long v = reset ? ds2::g_launches.exchange(0) : ds2::g_launches.load();
   return (int64_t)v;
+}
+
+// ---- side stream for deferred work (weight-gradient GEMMs of a recurrent layer run in the shadow of the NEXT layer's
+// latency-bound sweep, which leaves 20 of the 148 SMs and most of every pipe idle) ---------------------------------
+int ds2_set_side_stream(void* stream) {
+  ds2::g_side_stream.store(stream);
+  return DS2_OK;
+}
+
+// main `stream` waits for everything queued on the side stream so far (call before reading the deferred gradients)
+int ds2_join_side_stream(void* stream) {
+  using namespace ds2;
+  void* side = g_side_stream.load();
+  if (!side) return DS2_OK;
+  std::lock_guard<std::mutex> lk(g_side_mu);
+  if (!g_join_event) DS2_CHECK_CUDA(cudaEventCreateWithFlags(&g_join_event, cudaEventDisableTiming));
+  DS2_CHECK_CUDA(cudaEventRecord(g_join_event, as_stream(side)));
+  DS2_CHECK_CUDA(cudaStreamWaitEvent(as_stream(stream), g_join_event, 0));
+  return DS2_OK;
 }
 
 int64_t ds2_fallback_count(int reset) {

@@ -36,6 +36,13 @@ int device_sm_count();   // SM count of the current device (cached per device)
 // persistent sweeps): counted and reported once per shape on stderr, never silent.
 void note_fallback(const char* what, int rnn, int T, int B, int H, int D);
 
+// Optional side stream (ds2_set_side_stream): deferred work whose results nobody on the main stream needs before
+// ds2_join_side_stream.  Workspaces read by side work are protected by per-workspace events.
+extern std::atomic<void*> g_side_stream;
+int side_wait_for_workspace(const void* ws, cudaStream_t main);
+int side_fork(cudaStream_t main, cudaStream_t side);
+int side_mark_workspace(const void* ws, cudaStream_t side);
+
 #define DS2_CHECK_CUDA(expr)                                                             \
   do {                                                                                   \
     cudaError_t _e = (expr);                                                             \

@@ -83,45 +83,70 @@ __global__ void ctc_alpha_beta_kernel(int T, int B, int C, int Smax, const float
   const float* lpb = lp + (size_t)b * C;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nwarps = blockDim.x / 32;
 
-  int cur = 0;
-  for (int tt = 0; tt < Tb; ++tt) {
-    const int t = is_beta ? Tb - 1 - tt : tt;
-    const float* prev = buf + cur * W + 2;
-    float* next = buf + (cur ^ 1) * W + 2;
-    const float* lpt = lpb + (size_t)t * row_stride;
-    float local_max = -CUDART_INF_F;
-    for (int r = threadIdx.x; r < S; r += blockDim.x) {
-      const int l = ext[r];
-      float v;
-      if (tt == 0) {
-        v = (r < 2) ? lpt[l] : -CUDART_INF_F;
-      } else {
-        bool skip = (r >= 2) && (l != blank) && (l != ext[r - 2]);
-        float a2 = skip ? prev[r - 2] : -CUDART_INF_F;
-        v = lse3(prev[r], prev[r - 1], a2) + lpt[l];      // prev[-1], prev[-2] are the -inf guards
-      }
-      next[r] = v;
-      local_max = fmaxf(local_max, v);
-    }
-    if ((tt % RESCALE) == RESCALE - 1) {
+  // The log-probability a state adds at step t does not depend on the recursion: with one state per thread (the
+  // launcher's choice whenever 2L+1 <= 1024) the values of the NEXT block of 8 steps are fetched into registers while
+  // the current block runs (fully unrolled, no register rotation), so the ~600-cycle L2 latency of that load — a third
+  // of all stall samples in the round-1 kernel — is off the T-step dependency chain.
+  const bool one = S <= (int)blockDim.x;
+  const int l_own = (one && (int)threadIdx.x < S) ? ext[threadIdx.x] : blank;
+  float nxt[RESCALE];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) local_max = fmaxf(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
-      if (lane == 0) wmax[warp] = local_max;
-      __syncthreads();
-      float m = -CUDART_INF_F;
-      for (int w = 0; w < nwarps; ++w) m = fmaxf(m, wmax[w]);
-      if (m != -CUDART_INF_F) {
-        for (int r = threadIdx.x; r < S; r += blockDim.x) next[r] -= m;   // own states only
-        if (threadIdx.x == 0) shift_s += (double)m;
+  for (int i = 0; i < RESCALE; ++i) {
+    const int t_i = is_beta ? Tb - 1 - i : i;
+    nxt[i] = (one && i < Tb) ? lpb[(size_t)t_i * row_stride + l_own] : 0.f;
+  }
+  int cur = 0;
+  for (int t0 = 0; t0 < Tb; t0 += RESCALE) {
+    float lpv[RESCALE];
+#pragma unroll
+    for (int i = 0; i < RESCALE; ++i) {
+      lpv[i] = nxt[i];
+      const int ta = t0 + RESCALE + i, t_a = is_beta ? Tb - 1 - ta : ta;
+      nxt[i] = (one && ta < Tb) ? lpb[(size_t)t_a * row_stride + l_own] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < RESCALE; ++i) {
+      const int tt = t0 + i;
+      if (tt >= Tb) break;                               // block-uniform
+      const int t = is_beta ? Tb - 1 - tt : tt;
+      const float* prev = buf + cur * W + 2;
+      float* next = buf + (cur ^ 1) * W + 2;
+      const float* lpt = lpb + (size_t)t * row_stride;
+      float local_max = -CUDART_INF_F;
+      for (int r = threadIdx.x; r < S; r += blockDim.x) {
+        const int l = ext[r];
+        const float lpx = one ? lpv[i] : lpt[l];
+        float v;
+        if (tt == 0) {
+          v = (r < 2) ? lpx : -CUDART_INF_F;
+        } else {
+          bool skip = (r >= 2) && (l != blank) && (l != ext[r - 2]);
+          float a2 = skip ? prev[r - 2] : -CUDART_INF_F;
+          v = lse3(prev[r], prev[r - 1], a2) + lpx;       // prev[-1], prev[-2] are the -inf guards
+        }
+        next[r] = v;
+        local_max = fmaxf(local_max, v);
       }
+      if (i == RESCALE - 1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local_max = fmaxf(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+        if (lane == 0) wmax[warp] = local_max;
+        __syncthreads();
+        float m = -CUDART_INF_F;
+        for (int w = 0; w < nwarps; ++w) m = fmaxf(m, wmax[w]);
+        if (m != -CUDART_INF_F) {
+          for (int r = threadIdx.x; r < S; r += blockDim.x) next[r] -= m;   // own states only
+          if (threadIdx.x == 0) shift_s += (double)m;
+        }
+      }
+      for (int r = threadIdx.x; r < S; r += blockDim.x) {
+        int s = is_beta ? S - 1 - r : r;
+        table[(size_t)t * Smax + s] = next[r];
+      }
+      if (threadIdx.x == 0) offs[t] = shift_s;
+      __syncthreads();
+      cur ^= 1;
     }
-    for (int r = threadIdx.x; r < S; r += blockDim.x) {
-      int s = is_beta ? S - 1 - r : r;
-      table[(size_t)t * Smax + s] = next[r];
-    }
-    if (threadIdx.x == 0) offs[t] = shift_s;
-    __syncthreads();
-    cur ^= 1;
   }
   if (!is_beta && threadIdx.x == 0) {
     const float* last = buf + cur * W + 2;

@@ -306,24 +306,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (col0 >= N) break;              // warp-uniform
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * 256 + c * 32), v);
-        if (row < M) {
-          float* cp = C + (size_t)row * ldc + col0;
-          if (vec_ok && col0 + 32 <= N) {
+        if (vec_ok && col0 + 32 <= N) {
+          // A lane holds one accumulator row: storing from the registers would touch 32 rows x 16 bytes per
+          // instruction (the 524 MB projection output then runs at 1.6 TB/s and the tensor pipe idles 60 % of the
+          // kernel).  Turn the 32 x 32 block through shared memory — the pipeline stages are free once the accumulator
+          // barrier has completed — so that an instruction writes 4 rows x 128 contiguous bytes.
+          float* stg = reinterpret_cast<float*>(smem) + q * (32 * 36);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 o = make_float4(alpha * v[4 * j], alpha * v[4 * j + 1], alpha * v[4 * j + 2], alpha * v[4 * j + 3]);
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) =
+                make_float4(alpha * v[4 * j], alpha * v[4 * j + 1], alpha * v[4 * j + 2], alpha * v[4 * j + 3]);
+          __syncwarp();
+          const int c4 = lane & 7;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3), grow = m0 + mb * 128 + q * 32 + rr;
+            if (grow < M) {
+              float4 o = *reinterpret_cast<const float4*>(stg + rr * 36 + 4 * c4);
+              float* cp4 = C + (size_t)grow * ldc + col0 + 4 * c4;
               if (split) {
-                atomicAdd(reinterpret_cast<float4*>(cp + 4 * j), o);
+                atomicAdd(reinterpret_cast<float4*>(cp4), o);
               } else {
                 if (beta != 0.f) {
-                  float4 old = *reinterpret_cast<const float4*>(cp + 4 * j);
+                  const float4 old = *reinterpret_cast<const float4*>(cp4);
                   o.x = fmaf(beta, old.x, o.x); o.y = fmaf(beta, old.y, o.y);
                   o.z = fmaf(beta, old.z, o.z); o.w = fmaf(beta, old.w, o.w);
                 }
-                *reinterpret_cast<float4*>(cp + 4 * j) = o;
+                *reinterpret_cast<float4*>(cp4) = o;
               }
             }
-          } else {
+          }
+          __syncwarp();
+        } else if (row < M) {
+          float* cp = C + (size_t)row * ldc + col0;
+          {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < N) {

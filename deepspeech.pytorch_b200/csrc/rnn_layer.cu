@@ -391,6 +391,11 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
   if (rc) return rc;
   DS2_REQUIRE(ws_bytes >= ds2_rnn_workspace_bytes(d), "rnn bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
+  cudaStream_t side = as_stream(g_side_stream.load());
+  if (side) {   // deferred weight-gradient GEMMs of an earlier layer may still read operand copies in this workspace
+    rc = side_wait_for_workspace(ws, st);
+    if (rc) return rc;
+  }
   const int D = d->bidirectional ? 2 : 1, G = num_gates(d->rnn_type), T = d->T, B = d->B, In = d->In, H = d->H;
   const int TB = T * B, GH = G * H;
   Reserve R = carve_reserve(d, reserve);
@@ -500,6 +505,14 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
       if (rc) return rc;
     }
   }
+  // weight-gradient GEMMs: nobody needs dW_ih / dW_hh before the optimizer, so (precision-16 path, caller opted in)
+  // they go to the side stream, ordered after the sweep and the operand copies, and overlap the next layer's sweep
+  cudaStream_t gst = st;
+  if (f16 && side && d->deferred_dw) {
+    rc = side_fork(st, side);
+    if (rc) return rc;
+    gst = side;
+  }
   bool dx_done = false;
   if (f16 && dx) {   // dX = dG (TB x D*GH) . [W_ih fwd ; W_ih rev] : one K = D*G*H GEMM for both directions
     rc = gemm_tc_f16(TB, In, D * GH, 1.f, dG16, D * GH, w16T, D * GH, 0.f, bn_gamma ? dxbn : dx, In, scale + 1, st);
@@ -514,7 +527,7 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
     // dW_ih = dGx^T . xin
     rc = 1;
     if (f16) {
-      rc = gemm_tc_f16(GH, In, TB, 1.f, dG16T + (size_t)dir * GH * TB, TB, x16T, TB, 0.f, dw_ih[dir], In, scale + 1, st);
+      rc = gemm_tc_f16(GH, In, TB, 1.f, dG16T + (size_t)dir * GH * TB, TB, x16T, TB, 0.f, dw_ih[dir], In, scale + 1, gst);
       if (rc < 0) return rc;
     }
     if (rc == 1) rc = ds2_gemm(1, 0, GH, In, TB, 1.f, dG, ldg, xin, In, 0.f, dw_ih[dir], In, gws, gws_bytes, stream);
@@ -531,7 +544,7 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
       rc = 1;
       if (f16) {   // in the transposed copies a shift by one time step is a shift by B columns
         rc = gemm_tc_f16(rows_x, H, Kr, 1.f, dG16T + (size_t)dir * GH * TB + a_off, TB, h16T + (size_t)dir * H * TB + h_off,
-                         TB, 0.f, dw_hh[dir], H, scale + 1, st);
+                         TB, 0.f, dw_hh[dir], H, scale + 1, gst);
         if (rc < 0) return rc;
       }
       if (rc == 1)
@@ -542,7 +555,7 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
         rc = 1;
         if (f16) {
           rc = gemm_tc_f16(H, H, Kr, 1.f, aux16T + (size_t)dir * H * TB + a_off, TB, h16T + (size_t)dir * H * TB + h_off,
-                           TB, 0.f, dw_hh[dir] + (size_t)2 * H * H, H, scale + 1, st);
+                           TB, 0.f, dw_hh[dir] + (size_t)2 * H * H, H, scale + 1, gst);
           if (rc < 0) return rc;
         }
         if (rc == 1)
@@ -568,6 +581,10 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
                     gws, gws_bytes, stream);
       if (rc) return rc;
     }
+  }
+  if (gst != st) {
+    rc = side_mark_workspace(ws, side);
+    if (rc) return rc;
   }
   if (bn_gamma) {
     DS2_REQUIRE(dx && dbn_gamma && dbn_beta, "rnn bwd: BN layer needs dx, dbn_gamma, dbn_beta");

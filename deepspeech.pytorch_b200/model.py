@@ -169,7 +169,15 @@ class DeepSpeech(_Base):
         if hs is None:
             hs = [None] * len(self.rnns)
         new_hs = []
+        # dist.OverlappedGradAllReduce (gradient sinks on): the gradient of a block's INPUT exists only once the block's
+        # backward has run, i.e. once its parameter gradients are final in the flat buffer -> exchange them right away
+        bhook = getattr(self, "block_grad_hook", None) if training else None
+
+        def _mark(t, name):
+            if bhook is not None and t.requires_grad:
+                t.register_hook(lambda g, _n=name: bhook(_n))
         for i, layer in enumerate(self.rnns):
+            _mark(y, f"rnn{i}")
             h0 = c0 = None
             if hs[i] is not None:
                 if layer.rnn_code == _lib.RNN_LSTM:
@@ -184,6 +192,7 @@ class DeepSpeech(_Base):
             if bn is not None and training:
                 bn.num_batches_tracked += 1
             new_hs.append((hn, cn) if layer.rnn_code == _lib.RNN_LSTM else hn)
+        _mark(y, "head")
         if not self.bidirectional:
             y = ops.Lookahead.apply(y, self.lookahead[0].conv.weight)
         fbn, flin = self.fc[0].module[0], self.fc[0].module[1]

@@ -91,9 +91,11 @@ def _on_device(fn):
     return wrapped
 
 
-def workspace(nbytes, device):
-    """grow-only per-device scratch shared by all ops (they are stream-ordered)"""
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+def workspace(nbytes, device, slot=0):
+    """grow-only per-device scratch shared by all ops (they are stream-ordered).  Slots 1 and 2 alternate between
+    consecutive RnnLayer backwards while deferred weight-gradient GEMMs may still read the previous layer's operand
+    copies (the library orders the reuse of a slot after the side work that read it)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = None
@@ -101,6 +103,39 @@ def workspace(nbytes, device):
         ws = torch.empty(int(nbytes * 1.05) + 1024, dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
+
+
+# ---- deferred weight-gradient GEMMs (side stream) -------------------------------------------------------------------
+_side = {"stream": None, "slot": 0}
+
+
+def enable_deferred_weight_grads(device=None, enable=True):
+    """Let RnnLayer.backward queue dW_ih / dW_hh on a side stream so that they run in the shadow of the next layer's
+    latency-bound sweep (20 of the 148 SMs are idle there).  Effective only for parameters with registered gradient
+    sinks (FlatParams(direct_grads=True)): their memory is persistent, and whoever reads the gradients
+    (FusedOptimizer.step, OverlappedGradAllReduce) calls `join_deferred()` first.  Run the training loop on a stream
+    of higher priority than the side stream (`torch.cuda.Stream(priority=-1)`), otherwise a queued GEMM grid keeps the
+    next sweep from becoming resident and nothing overlaps."""
+    lib = get_lib()
+    if not enable:
+        _side["stream"] = None
+        check(lib.ds2_set_side_stream(None), "ds2_set_side_stream")
+        return None
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(dev):
+        _side["stream"] = torch.cuda.Stream(device=dev, priority=0)
+    check(lib.ds2_set_side_stream(C.c_void_p(_side["stream"].cuda_stream)), "ds2_set_side_stream")
+    return _side["stream"]
+
+
+def side_stream():
+    return _side["stream"]
+
+
+def join_deferred():
+    """order the current stream after every deferred weight-gradient GEMM queued so far"""
+    if _side["stream"] is not None:
+        check(get_lib().ds2_join_side_stream(_stream()), "ds2_join_side_stream")
 
 
 def _req(t, name):
@@ -228,7 +263,13 @@ class RnnLayer(torch.autograd.Function):
         dg, rdg = _out(ctx.sinks[0], bn_g) if ctx.has_bn else (None, None)
         db, rdb = _out(ctx.sinks[1], bn_b) if ctx.has_bn else (None, None)
         grads, rgrads = zip(*[_out(sk, w) for sk, w in zip(ctx.sinks[2:], weights)])
-        ws = workspace(lib.ds2_rnn_workspace_bytes(C.byref(desc)), dev)
+        slot = 0
+        desc.deferred_dw = 0
+        if _side["stream"] is not None and all(sk is not None for sk in ctx.sinks[2:]):
+            _side["slot"] ^= 1
+            slot = 1 + _side["slot"]
+            desc.deferred_dw = 1
+        ws = workspace(lib.ds2_rnn_workspace_bytes(C.byref(desc)), dev, slot)
         check(lib.ds2_rnn_layer_bwd(C.byref(desc), ptr(x), ptr(len_dev), ptr(bn_g), ptr(bn_b),
                                     ptr_array(weights[0::4]), ptr_array(weights[1::4]), ptr_array(weights[2::4]),
                                     ptr_array(weights[3::4]), ptr(dy), ptr(reserve), ptr(dx), ptr(dg), ptr(db),

@@ -63,6 +63,8 @@ class FusedOptimizer:
 
     def step(self, grad_scale: float = 1.0):
         with torch.cuda.device(self.flat.data.device):     # launches bind to the current device
+            from . import ops
+            ops.join_deferred()                            # weight-gradient GEMMs queued on the side stream
             self._step(grad_scale)
 
     def _step(self, grad_scale):

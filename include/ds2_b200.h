@@ -67,6 +67,15 @@ int64_t ds2_launch_count(int reset);
  * stderr): a benchmark line with a non-zero count did not run the path it claims.                      */
 int64_t ds2_fallback_count(int reset);
 
+/* Optional side stream for deferred work.  With a side stream set, ds2_rnn_layer_bwd(deferred_dw != 0) queues the
+ * weight-gradient GEMMs (dW_ih, dW_hh: nobody needs them before the optimizer / the gradient exchange) on it, ordered
+ * after the layer's sweep and operand copies; they then run in the shadow of the next layer's latency-bound sweep.
+ * The caller (a) alternates between two workspaces for consecutive layers (the library orders the reuse of a
+ * workspace after the side work that read it), (b) calls ds2_join_side_stream(stream) before anything on `stream`
+ * (or any other stream ordered after it) reads those gradients.  NULL disables (default).                      */
+int ds2_set_side_stream(void* stream);
+int ds2_join_side_stream(void* stream);
+
 /* Device-time ranges around the kernel groups of each block (cudaEvent pairs on the launching stream).
  * ds2_prof_report synchronises, writes "tag:total_ms:count;..." into buf and clears the records.     */
 int ds2_prof_enable(int on);
@@ -120,6 +129,7 @@ typedef struct {
   int T, B, In, H;
   int training;      /* BN batch statistics + reserve */
   float bn_momentum, bn_eps;
+  int deferred_dw;   /* bwd: 1 = dW_ih / dW_hh may be queued on the side stream (see ds2_set_side_stream) */
 } ds2_rnn_desc;
 
 size_t ds2_rnn_reserve_floats(const ds2_rnn_desc* d);

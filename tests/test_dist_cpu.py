@@ -56,6 +56,28 @@ def _worker(rank, world, port, out):
             tiny.front_end_grad_hook()          # what DeepSpeech.forward's tensor hook does during backward
         ex.finish()
         assert torch.allclose(flat.grad, torch.arange(flat.n, dtype=torch.float32) * sum(range(1, world + 1)))
+    # per-block exchange (gradient sinks on): head first, then one recurrent layer at a time, conv in finish();
+    # the union of the pieces must be the whole buffer, each element reduced exactly once
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Linear(5, 7)
+            self.rnns = torch.nn.Sequential(torch.nn.Linear(7, 9), torch.nn.Linear(9, 9), torch.nn.Linear(9, 4))
+            self.lookahead = torch.nn.Linear(4, 4)
+            self.fc = torch.nn.Linear(4, 3)
+    net = Net()
+    flat = FlatParams(net, direct_grads=True)
+    ex = D.OverlappedGradAllReduce(flat, net)
+    assert ex.per_block and net.block_grad_hook is not None
+    assert 0 < ex.split == ex.block_start["rnn0"] < ex.block_start["rnn1"] < ex.block_start["rnn2"] < ex.block_start["head"]
+    for order in (["head", "rnn2", "rnn1", "rnn0"], ["head", "rnn1"], []):
+        flat.grad.copy_(torch.arange(flat.n, dtype=torch.float32) * (rank + 1))
+        for name in order:
+            net.block_grad_hook(name)               # what DeepSpeech.forward's tensor hooks do during backward
+        if order:
+            net.front_end_grad_hook()
+        ex.finish()
+        assert torch.allclose(flat.grad, torch.arange(flat.n, dtype=torch.float32) * sum(range(1, world + 1))), order
     dist.destroy_process_group()
     out.put(rank)
 

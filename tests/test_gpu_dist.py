@@ -43,7 +43,7 @@ def _params():
     return ocfg, O.init_params(ocfg, seed=9)
 
 
-def _worker(rank, world, port, backend, q):
+def _worker(rank, world, port, backend, direct, q):
     try:
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -59,7 +59,7 @@ def _worker(rank, world, port, backend, q):
         ds.set_precision("fp32")
         _, P = _params()
         model = make_model(CFG["rnn_type"], True, CFG["H"], CFG["layers"], params=P, device=dev).train()
-        flat = FlatParams(model)
+        flat = FlatParams(model, direct_grads=direct)   # True: per-block exchange from the backward hooks
         opt = FusedOptimizer(flat, model.optim_cfg, max_norm=400.0)
         ex = D.OverlappedGradAllReduce(flat, model)
         x, targets, pct, tsz = _shard(rank)
@@ -82,8 +82,8 @@ def _worker(rank, world, port, backend, q):
         raise
 
 
-@pytest.mark.parametrize("backend", ["gloo", "nccl"])
-def test_two_rank_step_equals_oracle_mean_gradient(backend):
+@pytest.mark.parametrize("backend,direct", [("gloo", False), ("gloo", True), ("nccl", True)])
+def test_two_rank_step_equals_oracle_mean_gradient(backend, direct):
     if backend == "nccl" and torch.cuda.device_count() < 2:
         pytest.skip("NCCL needs one GPU per rank (bench.py --gpus 2/4/8 covers it on the 8-GPU box)")
     from oracle import ds2_oracle as O
@@ -91,7 +91,7 @@ def test_two_rank_step_equals_oracle_mean_gradient(backend):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, direct, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = {}
