@@ -496,7 +496,7 @@ def run_b200(args):
     traffic_db = {}
     try:   # DRAM bytes per launch from the committed ncu --set full captures (librispeech workload only)
         if args.workload == "librispeech" and B == 32:
-            traffic_db = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            traffic_db = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
     except Exception:
         traffic_db = {}
     for tag, nbytes in (("rnn_fwd_sweep", fwd_bytes), ("rnn_bwd_sweep", bwd_bytes)):

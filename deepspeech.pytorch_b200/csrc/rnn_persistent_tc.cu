@@ -351,10 +351,10 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
     }
   } else if (warp == 1) {
     if (RES) {
-      if (lane == 0) {
+      {   // the whole warp runs the issue loop converged (mma_f16_w: elect.sync inside), see tc_common.cuh
         const uint32_t idesc = instr_desc(FMT_F16, MM, NB);
-        const uint64_t a_base = smem_desc_sw128(smem_u32(smem));
-        const uint64_t b_base = smem_desc_sw128(smem_u32(smem + NKR * A_BYTES));
+        const uint64_t a_base = warp_uniform(smem_desc_sw128(smem_u32(smem)));
+        const uint64_t b_base = warp_uniform(smem_desc_sw128(smem_u32(smem + NKR * A_BYTES)));
         const uint64_t a_step = (uint64_t)(A_BYTES >> 4), b_step = (uint64_t)(B_BYTES >> 4);
         mbar_wait(&empty[0], 0);                 // weights resident
         uint32_t ph = 0;
@@ -362,27 +362,27 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
           for (int g = 0; g < NG; ++g) {
             mbar_wait(full + g, ph);
             tc_fence_after();
-            if (g == 0) trace_stamp(p.trace, p.T, step, 2);
+            if (g == 0 && lane == 0) trace_stamp(p.trace, p.T, step, 2);
             const int c0 = grp_begin(g), c1 = min(NKR, grp_begin(g + 1));
-            if (c1 == NKR) trace_stamp(p.trace, p.T, step, 3);
+            if (c1 == NKR && lane == 0) trace_stamp(p.trace, p.T, step, 3);
             for (int c = c0; c < c1; ++c) {
               const uint64_t ad = a_base + (uint64_t)c * a_step, bd = b_base + (uint64_t)c * b_step;
-              mma_f16(0u, ad, bd, idesc, c > 0);
-              mma_f16(0u, ad + 2, bd + 2, idesc, 1);
-              mma_f16(0u, ad + 4, bd + 4, idesc, 1);
-              mma_f16(0u, ad + 6, bd + 6, idesc, 1);
+              mma_f16_w(0u, ad, bd, idesc, c > 0);
+              mma_f16_w(0u, ad + 2, bd + 2, idesc, 1);
+              mma_f16_w(0u, ad + 4, bd + 4, idesc, 1);
+              mma_f16_w(0u, ad + 6, bd + 6, idesc, 1);
             }
           }
-          mma_commit(accum_bar);
-          trace_stamp(p.trace, p.T, step, 4);
+          mma_commit_w(accum_bar);
+          if (lane == 0) trace_stamp(p.trace, p.T, step, 4);
           ph ^= 1;
         }
       }
     } else
-    if (lane == 0) {
-      // The single issuing thread is the critical path of a step (measured: ~69 cycles per tcgen05.mma even
-      // in a minimal loop, ~280 with per-MMA descriptor arithmetic): keep the loop free of div/mod and
-      // descriptor construction.
+    {
+      // The issue chain is the critical path of a step: the whole warp runs it converged (mma_tf32_w: elect.sync
+      // inside; a single divergent lane costs ~70 cycles per tcgen05.mma, converged ~30-40) and the loop is free of
+      // div/mod and descriptor construction.
       const uint32_t idesc = instr_desc(FMT_TF32, MM, NB);
       const uint64_t a_base = smem_desc_sw128(smem_u32(smem));
       const uint64_t b_base = smem_desc_sw128(smem_u32(smem + A_BYTES));
@@ -392,18 +392,18 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_persist_kernel(const _
       for (int step = 1; step < T; ++step) {
         for (int c = 0; c < NK; ++c) {
           mbar_wait(&full[s], ph);
-          if (c == 0) trace_stamp(p.trace, p.T, step, 1);
-          if (c == NK - 1) trace_stamp(p.trace, p.T, step, 2);
+          if (c == 0 && lane == 0) trace_stamp(p.trace, p.T, step, 1);
+          if (c == NK - 1 && lane == 0) trace_stamp(p.trace, p.T, step, 2);
           tc_fence_after();
           const uint64_t ad = a_base + (uint64_t)s * stage_step, bd = b_base + (uint64_t)s * stage_step;
-          mma_tf32(0u, ad, bd, idesc, c > 0);
-          mma_tf32(0u, ad + 2, bd + 2, idesc, 1);
-          mma_tf32(0u, ad + 4, bd + 4, idesc, 1);
-          mma_tf32(0u, ad + 6, bd + 6, idesc, 1);
-          mma_commit(&empty[s]);
+          mma_tf32_w(0u, ad, bd, idesc, c > 0);
+          mma_tf32_w(0u, ad + 2, bd + 2, idesc, 1);
+          mma_tf32_w(0u, ad + 4, bd + 4, idesc, 1);
+          mma_tf32_w(0u, ad + 6, bd + 6, idesc, 1);
+          mma_commit_w(&empty[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        mma_commit(accum_bar);
+        mma_commit_w(accum_bar);
       }
     }
   } else {
@@ -910,10 +910,10 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // The single issuing thread is the critical path of a step (measured: ~69 cycles per tcgen05.mma even
-      // in a minimal loop, ~280 with per-MMA descriptor arithmetic): keep the loop free of div/mod and
-      // descriptor construction.
+    {
+      // The issue chain is the critical path of a step: the whole warp runs it converged (mma_tf32_w: elect.sync
+      // inside; a single divergent lane costs ~70 cycles per tcgen05.mma, converged ~30-40) and the loop is free of
+      // div/mod and descriptor construction.
       const uint32_t idesc = instr_desc(FMT_TF32, MM, NB);
       const uint64_t a_base = smem_desc_sw128(smem_u32(smem));
       const uint64_t b_base = smem_desc_sw128(smem_u32(smem + A_BYTES));
@@ -923,18 +923,18 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_persist_kernel(const _
       for (int step = 1; step < T; ++step) {
         for (int c = 0; c < NK; ++c) {
           mbar_wait(&full[s], ph);
-          if (c == 0) trace_stamp(p.trace, p.T, step, 1);
-          if (c == NK - 1) trace_stamp(p.trace, p.T, step, 2);
+          if (c == 0 && lane == 0) trace_stamp(p.trace, p.T, step, 1);
+          if (c == NK - 1 && lane == 0) trace_stamp(p.trace, p.T, step, 2);
           tc_fence_after();
           const uint64_t ad = a_base + (uint64_t)s * stage_step, bd = b_base + (uint64_t)s * stage_step;
-          mma_tf32(0u, ad, bd, idesc, c > 0);
-          mma_tf32(0u, ad + 2, bd + 2, idesc, 1);
-          mma_tf32(0u, ad + 4, bd + 4, idesc, 1);
-          mma_tf32(0u, ad + 6, bd + 6, idesc, 1);
-          mma_commit(&empty[s]);
+          mma_tf32_w(0u, ad, bd, idesc, c > 0);
+          mma_tf32_w(0u, ad + 2, bd + 2, idesc, 1);
+          mma_tf32_w(0u, ad + 4, bd + 4, idesc, 1);
+          mma_tf32_w(0u, ad + 6, bd + 6, idesc, 1);
+          mma_commit_w(&empty[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        mma_commit(accum_bar);
+        mma_commit_w(accum_bar);
       }
     }
   } else {
@@ -1235,10 +1235,11 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
     }
   } else if (warp == 1) {
     if (RES) {
-      if (lane == 0) {
+      {   // the whole warp runs the issue loop converged (mma_f16_w: elect.sync inside): 64 MMAs per step in ~1.9k
+          // cycles instead of ~4.9k from a single divergent lane
         const uint32_t idesc = instr_desc(FMT_F16, UM, NB);
-        const uint64_t a_base = smem_desc_sw128(smem_u32(smem));
-        const uint64_t b_base = smem_desc_sw128(smem_u32(smem + NKR * A_BYTES));
+        const uint64_t a_base = warp_uniform(smem_desc_sw128(smem_u32(smem)));
+        const uint64_t b_base = warp_uniform(smem_desc_sw128(smem_u32(smem + NKR * A_BYTES)));
         const uint64_t a_step = (uint64_t)(A_BYTES >> 4), b_step = (uint64_t)(B_BYTES >> 4);
         mbar_wait(&empty[0], 0);
         uint32_t ph = 0;
@@ -1246,24 +1247,24 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
           for (int g = 0; g < NG; ++g) {
             mbar_wait(full + g, ph);
             tc_fence_after();
-            if (g == 0) trace_stamp(p.trace, p.T, step, 2);
+            if (g == 0 && lane == 0) trace_stamp(p.trace, p.T, step, 2);
             const int c0 = grp_begin(g), c1 = min(NKR, grp_begin(g + 1));
-            if (c1 == NKR) trace_stamp(p.trace, p.T, step, 3);
+            if (c1 == NKR && lane == 0) trace_stamp(p.trace, p.T, step, 3);
             for (int c = c0; c < c1; ++c) {
               const uint64_t ad = a_base + (uint64_t)c * a_step, bd = b_base + (uint64_t)c * b_step;
-              mma_f16(0u, ad, bd, idesc, c > 0);
-              mma_f16(0u, ad + 2, bd + 2, idesc, 1);
-              mma_f16(0u, ad + 4, bd + 4, idesc, 1);
-              mma_f16(0u, ad + 6, bd + 6, idesc, 1);
+              mma_f16_w(0u, ad, bd, idesc, c > 0);
+              mma_f16_w(0u, ad + 2, bd + 2, idesc, 1);
+              mma_f16_w(0u, ad + 4, bd + 4, idesc, 1);
+              mma_f16_w(0u, ad + 6, bd + 6, idesc, 1);
             }
           }
-          mma_commit(accum_bar);
-          trace_stamp(p.trace, p.T, step, 4);
+          mma_commit_w(accum_bar);
+          if (lane == 0) trace_stamp(p.trace, p.T, step, 4);
           ph ^= 1;
         }
       }
     } else
-    if (lane == 0) {
+    {   // converged issue, see mma_tf32_w
       const uint32_t idesc = instr_desc(FMT_TF32, UM, NB);
       const uint64_t a_base = smem_desc_sw128(smem_u32(smem));
       const uint64_t b_base = smem_desc_sw128(smem_u32(smem + A_BYTES));
@@ -1273,18 +1274,18 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
       for (int step = 1; step < T; ++step) {
         for (int c = 0; c < NK; ++c) {
           mbar_wait(&full[s], ph);
-          if (c == 0) trace_stamp(p.trace, p.T, step, 1);
-          if (c == NK - 1) trace_stamp(p.trace, p.T, step, 2);
+          if (c == 0 && lane == 0) trace_stamp(p.trace, p.T, step, 1);
+          if (c == NK - 1 && lane == 0) trace_stamp(p.trace, p.T, step, 2);
           tc_fence_after();
           const uint64_t ad = a_base + (uint64_t)s * stage_step, bd = b_base + (uint64_t)s * stage_step;
-          mma_tf32(0u, ad, bd, idesc, c > 0);
-          mma_tf32(0u, ad + 2, bd + 2, idesc, 1);
-          mma_tf32(0u, ad + 4, bd + 4, idesc, 1);
-          mma_tf32(0u, ad + 6, bd + 6, idesc, 1);
-          mma_commit(&empty[s]);
+          mma_tf32_w(0u, ad, bd, idesc, c > 0);
+          mma_tf32_w(0u, ad + 2, bd + 2, idesc, 1);
+          mma_tf32_w(0u, ad + 4, bd + 4, idesc, 1);
+          mma_tf32_w(0u, ad + 6, bd + 6, idesc, 1);
+          mma_commit_w(&empty[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        mma_commit(accum_bar);
+        mma_commit_w(accum_bar);
       }
     }
   } else {
@@ -1785,10 +1786,11 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // the whole warp runs the issue loop converged (mma_f16_w: elect.sync inside): 32 MMAs per step in ~1.2k
+        // cycles instead of ~2.4k from a single divergent lane
       const uint32_t idesc = instr_desc(FMT_F16, 128, NB);
-      const uint64_t a_base = smem_desc_sw128(smem_u32(smem));
-      const uint64_t b_base = smem_desc_sw128(smem_u32(smem + NKR * AW));
+      const uint64_t a_base = warp_uniform(smem_desc_sw128(smem_u32(smem)));
+      const uint64_t b_base = warp_uniform(smem_desc_sw128(smem_u32(smem + NKR * AW)));
       const uint64_t a_step = (uint64_t)(AW >> 4), b_step = (uint64_t)(B_BYTES >> 4);
       mbar_wait(wbar, 0);
       uint32_t ph = 0;
@@ -1796,19 +1798,19 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __
         for (int g = 0; g < NG; ++g) {
           mbar_wait(full + g, ph);
           tc_fence_after();
-          if (g == 0) trace_stamp(p.trace, p.T, step, 2);
+          if (g == 0 && lane == 0) trace_stamp(p.trace, p.T, step, 2);
           const int c0 = grp_begin(g), c1 = min(NKR, grp_begin(g + 1));
-          if (c1 == NKR) trace_stamp(p.trace, p.T, step, 3);
+          if (c1 == NKR && lane == 0) trace_stamp(p.trace, p.T, step, 3);
           for (int c = c0; c < c1; ++c) {
             const uint64_t ad = a_base + (uint64_t)c * a_step, bd = b_base + (uint64_t)c * b_step;
-            mma_f16(0u, ad, bd, idesc, c > 0);
-            mma_f16(0u, ad + 2, bd + 2, idesc, 1);
-            mma_f16(0u, ad + 4, bd + 4, idesc, 1);
-            mma_f16(0u, ad + 6, bd + 6, idesc, 1);
+            mma_f16_w(0u, ad, bd, idesc, c > 0);
+            mma_f16_w(0u, ad + 2, bd + 2, idesc, 1);
+            mma_f16_w(0u, ad + 4, bd + 4, idesc, 1);
+            mma_f16_w(0u, ad + 6, bd + 6, idesc, 1);
           }
         }
-        mma_commit(accum_bar);
-        trace_stamp(p.trace, p.T, step, 4);
+        mma_commit_w(accum_bar);
+        if (lane == 0) trace_stamp(p.trace, p.T, step, 4);
         ph ^= 1;
       }
     }

@@ -427,14 +427,15 @@ def test_direct_gradient_sinks_equal_autograd_accumulation(rnn_type, bidir):
 
 def test_deferred_weight_gradient_gemms_give_the_same_gradients():
     """precision-16 mode with gradient sinks: dW_ih / dW_hh of every recurrent layer queued on the side stream (two
-    alternating operand workspaces, join before the optimizer) vs everything on the compute stream.  The GEMMs are
-    the same kernels on the same operands: the flat gradient buffer and the parameters after one fused AdamW step
-    must be bit-identical."""
+    alternating operand workspaces, join before the gradients are read) vs everything on the compute stream.  The
+    GEMMs are the same kernels on the same operands: the flat gradient buffer must agree to the level of the float
+    atomics' run-to-run noise, on the first backward and on a second one from the same parameters (workspace slots
+    reused, gradients overwritten)."""
     from deepspeech_pytorch_b200.optim import FlatParams, FusedOptimizer
     ds.set_precision("fp16")
     ocfg = oracle_cfg("lstm", True, 128, 3)
     P = O.init_params(ocfg, seed=13)
-    x, targets, pct, tsz = O.synth_batch(8, 200, seed=3, lmin=5, lmax=20)
+    batches = [O.synth_batch(8, 200, seed=s_, lmin=5, lmax=20) for s_ in (3, 4)]
     out = {}
     try:
         for defer in (False, True):
@@ -443,21 +444,25 @@ def test_deferred_weight_gradient_gemms_give_the_same_gradients():
             opt = FusedOptimizer(flat, model.optim_cfg)
             main = torch.cuda.Stream(priority=-1)
             main.wait_stream(torch.cuda.current_stream())
+            gs = []
             with torch.cuda.stream(main):
                 ds.ops.enable_deferred_weight_grads(enable=defer)
-                for _ in range(2):                       # second step: workspace slots are reused
+                for x, targets, pct, tsz in batches:         # same parameters for both backwards
+                    model.load_state_dict(P)                 # (undo the running-statistics update)
                     model.training_step((x.cuda(), targets, pct.clone(), tsz), 0).backward()
                     ds.ops.join_deferred()
-                    g = flat.grad.clone()
-                    opt.step()
+                    gs.append(flat.grad.clone())
+                before = flat.data.clone()
+                opt.step()                                   # joins by itself
             torch.cuda.synchronize()
-            out[defer] = (g, flat.data.clone())
+            assert not torch.equal(before, flat.data)
+            out[defer] = gs
             del model, flat, opt
     finally:
         ds.ops.enable_deferred_weight_grads(enable=False)
         ds.set_precision("fp32")
-    # (the BatchNorm / column-sum reductions use float atomics: run-to-run differences in the last bits are expected,
-    # a missing dependency would show up as stale or partial gradients, orders of magnitude above this bound)
-    assert rel(out[True][0], out[False][0]) < 1e-5 and rel_l2(out[True][0], out[False][0]) < 1e-6
-    assert rel(out[True][1], out[False][1]) < 1e-6
-    assert float(out[True][0].abs().max()) > 0
+    # (the BatchNorm / column-sum reductions use float atomics: run-to-run differences in the last bits are expected; a
+    # missing dependency would show up as stale or partial gradients, orders of magnitude above this bound)
+    for a, b in zip(out[True], out[False]):
+        assert rel(a, b) < 1e-5 and rel_l2(a, b) < 1e-6
+    assert rel(out[True][0], out[True][1]) > 1e-2
