@@ -1100,7 +1100,7 @@ __device__ __forceinline__ float pow2f(int ex) { return __int_as_float((ex + 127
 // number of CTAs, but each reduces only K/8, i.e. half as many MMA instructions on the per-step critical path).
 // LL (RES only): no grid barrier; the scaled fp16 gate gradients are their own ready flags (see the LL helpers) and
 // the per-step maxima travel as one word per (CTA, epilogue warp) in `gmeta`.
-template <int RNN, bool RES, int CL, bool LL = false>
+template <int RNN, bool RES, int CL, bool LL = false, int NKR_T = 0>   // NKR_T: see rnn_fwd_splitk_kernel
 __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __grid_constant__ PersistParams p) {
   using namespace rp;
   using namespace tc;
@@ -1113,7 +1113,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
   const int NB = p.NB, B = p.B, T = p.T, H = p.H, D = p.D;
   const int B_BYTES = NB * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   const int NBp = NB + 1;
-  const int NKR = (G * H / CL) / 64;                                     // resident: 64 fp16 of K per chunk
+  const int NKR = NKR_T ? NKR_T : (G * H / CL) / 64;                     // resident: 64 fp16 of K per chunk
   const int NG = grp_count(NKR);
   const int ring_bytes = RES ? NKR * STAGE_BYTES : STAGES * STAGE_BYTES;
   float* part = reinterpret_cast<float*>(smem + ring_bytes);             // [CL sources] partial dh_rec tiles (xt_* layout)
@@ -1244,18 +1244,37 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
         mbar_wait(&empty[0], 0);
         uint32_t ph = 0;
         for (int step = 1; step < T; ++step) {
-          for (int g = 0; g < NG; ++g) {
-            mbar_wait(full + g, ph);
-            tc_fence_after();
-            if (g == 0 && lane == 0) trace_stamp(p.trace, p.T, step, 2);
-            const int c0 = grp_begin(g), c1 = min(NKR, grp_begin(g + 1));
-            if (c1 == NKR && lane == 0) trace_stamp(p.trace, p.T, step, 3);
-            for (int c = c0; c < c1; ++c) {
-              const uint64_t ad = a_base + (uint64_t)c * a_step, bd = b_base + (uint64_t)c * b_step;
-              mma_f16_w(0u, ad, bd, idesc, c > 0);
-              mma_f16_w(0u, ad + 2, bd + 2, idesc, 1);
-              mma_f16_w(0u, ad + 4, bd + 4, idesc, 1);
-              mma_f16_w(0u, ad + 6, bd + 6, idesc, 1);
+          if constexpr (NKR_T > 0) {
+            constexpr int NGT = (NKR_T + 3) / 4;
+#pragma unroll
+            for (int g = 0; g < NGT; ++g) {
+              mbar_wait(full + g, ph);
+              tc_fence_after();
+              if (g == 0 && lane == 0) trace_stamp(p.trace, p.T, step, 2);
+              if (g == NGT - 1 && lane == 0) trace_stamp(p.trace, p.T, step, 3);
+#pragma unroll
+              for (int c = 4 * g; c < (4 * g + 4 < NKR_T ? 4 * g + 4 : NKR_T); ++c) {
+                const uint64_t ad = a_base + (uint64_t)c * a_step, bd = b_base + (uint64_t)c * b_step;
+                mma_f16_w(0u, ad, bd, idesc, c > 0);
+                mma_f16_w(0u, ad + 2, bd + 2, idesc, 1);
+                mma_f16_w(0u, ad + 4, bd + 4, idesc, 1);
+                mma_f16_w(0u, ad + 6, bd + 6, idesc, 1);
+              }
+            }
+          } else {
+            for (int g = 0; g < NG; ++g) {
+              mbar_wait(full + g, ph);
+              tc_fence_after();
+              if (g == 0 && lane == 0) trace_stamp(p.trace, p.T, step, 2);
+              const int c0 = grp_begin(g), c1 = min(NKR, grp_begin(g + 1));
+              if (c1 == NKR && lane == 0) trace_stamp(p.trace, p.T, step, 3);
+              for (int c = c0; c < c1; ++c) {
+                const uint64_t ad = a_base + (uint64_t)c * a_step, bd = b_base + (uint64_t)c * b_step;
+                mma_f16_w(0u, ad, bd, idesc, c > 0);
+                mma_f16_w(0u, ad + 2, bd + 2, idesc, 1);
+                mma_f16_w(0u, ad + 4, bd + 4, idesc, 1);
+                mma_f16_w(0u, ad + 6, bd + 6, idesc, 1);
+              }
             }
           }
           mma_commit_w(accum_bar);
@@ -1694,7 +1713,9 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_bwd_splitk_kernel(const __
 // epilogue warp pushes its 32 accumulator rows into the owner's shared memory with st.async (complete_tx on
 // the owner's mbarrier); the owner adds the two partial tiles, the input projection and the biases, and runs
 // gates + cell update for its 16 units in one pass (thread = 4 consecutive units x one batch column).
-template <int RNN, bool LL>
+// NKR_T: compile-time number of K chunks per CTA (0 = runtime): with constant chunk offsets the MMA descriptors are
+// "uniform base + immediate" and the issue loop needs no vector arithmetic / R2UR per instruction.
+template <int RNN, bool LL, int NKR_T = 0>
 __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __grid_constant__ PersistParams p) {
   using namespace rp;
   using namespace tc;
@@ -1705,7 +1726,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __
   const int NB = p.NB, B = p.B, T = p.T, H = p.H, D = p.D;
   const int B_BYTES = NB * 128;
   const int NBp = NB + 1;
-  const int NKR = H / 128;                               // 64-wide fp16 chunks of this CTA's K half
+  const int NKR = NKR_T ? NKR_T : H / 128;               // 64-wide fp16 chunks of this CTA's K half
   const int NG = grp_count(NKR);
   float* part = reinterpret_cast<float*>(smem + NKR * (AW + B_BYTES));   // [2 sources] 64-row partial tiles (xt_* layout)
   float* cst = part + 2 * xt_slice(64, NB);                              // [16][NBp] cell (LSTM) / hidden (GRU) state
@@ -1795,18 +1816,37 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rnn_fwd_splitk_kernel(const __
       mbar_wait(wbar, 0);
       uint32_t ph = 0;
       for (int step = 1; step < T; ++step) {
-        for (int g = 0; g < NG; ++g) {
-          mbar_wait(full + g, ph);
-          tc_fence_after();
-          if (g == 0 && lane == 0) trace_stamp(p.trace, p.T, step, 2);
-          const int c0 = grp_begin(g), c1 = min(NKR, grp_begin(g + 1));
-          if (c1 == NKR && lane == 0) trace_stamp(p.trace, p.T, step, 3);
-          for (int c = c0; c < c1; ++c) {
-            const uint64_t ad = a_base + (uint64_t)c * a_step, bd = b_base + (uint64_t)c * b_step;
-            mma_f16_w(0u, ad, bd, idesc, c > 0);
-            mma_f16_w(0u, ad + 2, bd + 2, idesc, 1);
-            mma_f16_w(0u, ad + 4, bd + 4, idesc, 1);
-            mma_f16_w(0u, ad + 6, bd + 6, idesc, 1);
+        if constexpr (NKR_T > 0) {
+          constexpr int NGT = (NKR_T + 3) / 4;
+#pragma unroll
+          for (int g = 0; g < NGT; ++g) {
+            mbar_wait(full + g, ph);
+            tc_fence_after();
+            if (g == 0 && lane == 0) trace_stamp(p.trace, p.T, step, 2);
+            if (g == NGT - 1 && lane == 0) trace_stamp(p.trace, p.T, step, 3);
+#pragma unroll
+            for (int c = 4 * g; c < (4 * g + 4 < NKR_T ? 4 * g + 4 : NKR_T); ++c) {
+              const uint64_t ad = a_base + (uint64_t)c * a_step, bd = b_base + (uint64_t)c * b_step;
+              mma_f16_w(0u, ad, bd, idesc, c > 0);
+              mma_f16_w(0u, ad + 2, bd + 2, idesc, 1);
+              mma_f16_w(0u, ad + 4, bd + 4, idesc, 1);
+              mma_f16_w(0u, ad + 6, bd + 6, idesc, 1);
+            }
+          }
+        } else {
+          for (int g = 0; g < NG; ++g) {
+            mbar_wait(full + g, ph);
+            tc_fence_after();
+            if (g == 0 && lane == 0) trace_stamp(p.trace, p.T, step, 2);
+            const int c0 = grp_begin(g), c1 = min(NKR, grp_begin(g + 1));
+            if (c1 == NKR && lane == 0) trace_stamp(p.trace, p.T, step, 3);
+            for (int c = c0; c < c1; ++c) {
+              const uint64_t ad = a_base + (uint64_t)c * a_step, bd = b_base + (uint64_t)c * b_step;
+              mma_f16_w(0u, ad, bd, idesc, c > 0);
+              mma_f16_w(0u, ad + 2, bd + 2, idesc, 1);
+              mma_f16_w(0u, ad + 4, bd + 4, idesc, 1);
+              mma_f16_w(0u, ad + 6, bd + 6, idesc, 1);
+            }
           }
         }
         mma_commit_w(accum_bar);
@@ -2073,10 +2113,11 @@ static int launch_fwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
   p.h16 = reinterpret_cast<__half*>(static_cast<char*>(ws) + 4096 + align_up((size_t)a.D * G * a.H * a.H * 2, 256));
   const size_t smem = one_cta_per_sm(fwd_splitk_smem_bytes(p.NB, a.H));
   if (smem > 227 * 1024) return 1;
-  auto kern = rnn_fwd_splitk_kernel<RNN, LL>;
+  auto kern = (a.H == 1024) ? rnn_fwd_splitk_kernel<RNN, LL, 8> : rnn_fwd_splitk_kernel<RNN, LL, 0>;   // H = 1024: unrolled issue loop
   static DeviceOnce attr_once;
-  if (attr_once.first()) {
-    DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (attr_once.first()) {   // BOTH instantiations: whichever shape comes first must not leave the other without its opt-in
+    DS2_CHECK_CUDA(cudaFuncSetAttribute(rnn_fwd_splitk_kernel<RNN, LL, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DS2_CHECK_CUDA(cudaFuncSetAttribute(rnn_fwd_splitk_kernel<RNN, LL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_once.done();
   }
   int grid = a.D * p.NT * 2, launches = 1;
@@ -2125,7 +2166,11 @@ static int launch_fwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
     cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
     if (le != cudaSuccess) {
       (void)cudaGetLastError();
-      if (li == 0) return 1;
+      if (li == 0) {
+        fprintf(stderr, "ds2_b200: WARNING split-K forward sweep launch failed (%s); using the 16-unit kernel\n",
+                cudaGetErrorString(le));
+        return 1;
+      }
       set_error("split-K forward sweep: second launch failed: %s", cudaGetErrorString(le));
       return DS2_ERR_CUDA;
     }
@@ -2224,10 +2269,13 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
   p.dg16 = reinterpret_cast<__half*>(base + off);
   const size_t smem = one_cta_per_sm(splitk_res_smem_bytes(p.NB, GH / CL, CL));
   if (smem > 227 * 1024) return 1;
-  auto kern = rnn_bwd_splitk_kernel<RNN, true, CL, LL>;
+  // H = 1024 (the BASELINE shapes): compile-time chunk count -> unrolled issue loop
+  constexpr int NKU = (G * 1024 / CL) / 64;   // chunks per CTA at H = 1024: 16 / 12 / 4 (CL 4), 8 / 6 / 2 (CL 8)
+  auto kern = (!LL && a.H == 1024) ? rnn_bwd_splitk_kernel<RNN, true, CL, LL, NKU> : rnn_bwd_splitk_kernel<RNN, true, CL, LL, 0>;
   static DeviceOnce attr_once;
-  if (attr_once.first()) {
-    DS2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (attr_once.first()) {   // BOTH instantiations (see the forward launcher)
+    DS2_CHECK_CUDA(cudaFuncSetAttribute(rnn_bwd_splitk_kernel<RNN, true, CL, LL, NKU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DS2_CHECK_CUDA(cudaFuncSetAttribute(rnn_bwd_splitk_kernel<RNN, true, CL, LL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_once.done();
   }
   int grid = a.D * p.NT * CL, launches = 1;
@@ -2281,7 +2329,12 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
     cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
     if (le != cudaSuccess) {
       (void)cudaGetLastError();
-      if (li == 0) return 1;
+      if (li == 0) {
+        if (CL != 8)
+          fprintf(stderr, "ds2_b200: WARNING resident split-K backward sweep launch failed (%s); using a slower variant\n",
+                  cudaGetErrorString(le));
+        return 1;
+      }
       set_error("resident split-K backward sweep: second launch failed: %s", cudaGetErrorString(le));
       return DS2_ERR_CUDA;
     }

@@ -161,12 +161,17 @@ def test_sweeps_are_bit_repeatable():
     rnn, bidir, T, B, In, H = "lstm", True, 150, 32, 256, 1024
     x, lens, P, dy = _layer_case(rnn, bidir, T, B, In, H, seed=29)
     first = _run_b200(rnn, bidir, x, lens, P, dy)
+    bad = []
     for it in range(19):
         again = _run_b200(rnn, bidir, x, lens, P, dy)
         for n in ("y", "hn", "cn", "dx"):
-            assert torch.equal(first[n], again[n]), (it, n)
+            if not torch.equal(first[n], again[n]):
+                bad.append((it, n, float((first[n] - again[n]).abs().max())))
         for k in first["grads"]:
-            assert torch.equal(first["grads"][k], again["grads"][k]), (it, k)
+            a, b = first["grads"][k], again["grads"][k]
+            if not torch.equal(a, b):
+                bad.append((it, k.replace("rnns.0.rnn.", ""), float((a - b).abs().max()), int((a != b).sum())))
+    assert not bad, bad[:40]
 
 
 def test_full_model_tf32_logits_within_north_star_bound():
