@@ -55,6 +55,7 @@ PROTOTYPES = {
     "ds2_sgd_nesterov_step": (i32, [i64] + [vp] * 3 + [f32] * 3 + [i32, f32, f32, vp, vp, vp]),
     "ds2_gemm_workspace_bytes": (sz, [i32] * 5),
     "ds2_gemm": (i32, [i32] * 5 + [f32, vp, i32, vp, i32, f32, vp, i32, vp, sz, vp]),
+    "ds2_gemm_f16": (i32, [i32] * 3 + [f32, vp, i32, vp, i32, f32, vp, i32, vp]),
 }
 
 _lib = None

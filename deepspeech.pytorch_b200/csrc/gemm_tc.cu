@@ -714,6 +714,15 @@ int gemm_tc_f16(int M, int N, int K, float alpha, const void* A16, int lda, cons
     if (tiles2 >= 90) cfg = 2;
     else if (tiles2 * 2 >= 100 && tiles2 * 2 <= 148 && K >= 4096 && (beta == 0.f || beta == 1.f)) { cfg = 2; splits = 2; }
   }
+  // short K, large output (the input projection: K = 1024, 524 MB of fp32 C): the main loop of a 256 x 256 tile is 16
+  // stages, shorter than its epilogue — 128 x 256 tiles with TWO CTAs per SM let one CTA's epilogue overlap the other's
+  // main loop (DS2_GEMM16_CFG forces 1 / 2 / 3)
+  if (cfg == 2 && splits == 1 && K <= 2048 && tiles2 >= 4 * 148) cfg = 3;
+  {
+    const char* e = getenv("DS2_GEMM16_CFG");
+    const int forced = e ? atoi(e) : 0;
+    if (forced >= 1 && forced <= 3 && !(forced == 2 && M < 256)) { cfg = forced; if (forced != 2) splits = 1; }
+  }
   const int bm = cfg == 2 ? 256 : 128;
   CUtensorMap tmA, tmB;
   int rc = make_tmap_f16(&tmA, A16, 2, K, M, 1, (size_t)lda, 0, 64, bm, 1);
@@ -721,6 +730,7 @@ int gemm_tc_f16(int M, int N, int K, float alpha, const void* A16, int lda, cons
   rc = make_tmap_f16(&tmB, B16, 2, K, N, 1, (size_t)ldb, 0, 64, gtc::BN, 1);
   if (rc) return rc;
   if (cfg == 2) return launch_gemm_tc<false, false, 2, 3, true>(tmA, tmB, M, N, K, alpha, beta, C, ldc, 0, splits, st, alpha_dev);
+  if (cfg == 3) return launch_gemm_tc<false, false, 1, 2, true>(tmA, tmB, M, N, K, alpha, beta, C, ldc, 0, splits, st, alpha_dev);
   return launch_gemm_tc<false, false, 1, 4, true>(tmA, tmB, M, N, K, alpha, beta, C, ldc, 0, splits, st, alpha_dev);
 }
 

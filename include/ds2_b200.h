@@ -221,6 +221,11 @@ int ds2_gemm(int transA, int transB, int M, int N, int K, float alpha, const flo
              const float* B, int ldb, float beta, float* C, int ldc,
              void* workspace, size_t workspace_bytes, void* stream);
 
+/* fp16-operand variant (the precision-16 mode's GEMM): A16 (M,K) and B16 (N,K) are K-major half matrices on the
+ * device, C = alpha * A16 . B16^T + beta * C in fp32.  lda / ldb multiples of 8, 16-byte aligned bases.       */
+int ds2_gemm_f16(int M, int N, int K, float alpha, const void* A16, int lda, const void* B16, int ldb, float beta,
+                 float* C, int ldc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -466,3 +466,23 @@ def test_deferred_weight_gradient_gemms_give_the_same_gradients():
     for a, b in zip(out[True], out[False]):
         assert rel(a, b) < 1e-5 and rel_l2(a, b) < 1e-6
     assert rel(out[True][0], out[True][1]) > 1e-2
+
+
+@pytest.mark.parametrize("cfg", ["1", "2", "3"])
+def test_gemm_f16_tile_configurations_vs_fp64(cfg, monkeypatch):
+    """the precision-16 mode's GEMM (fp16 K-major operands, fp32 accumulation) in every tile configuration, incl. the
+    2-CTAs-per-SM one the short-K projection shape selects, a K tail (K % 64 != 0), split-K and alpha / beta"""
+    import ctypes as C
+    monkeypatch.setenv("DS2_GEMM16_CFG", cfg)
+    lib = ds.get_lib()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for M, N, K, alpha, beta in [(640, 520, 1000, 1.0, 0.0), (4096, 1024, 4104, 0.5, 1.0), (300, 96, 72, 1.0, 0.0)]:
+        a = (torch.randn(M, K, generator=g, device="cuda")).half()
+        b = (torch.randn(N, K, generator=g, device="cuda")).half()
+        c0 = torch.randn(M, N, generator=g, device="cuda")
+        out = c0.clone()
+        rc = lib.ds2_gemm_f16(M, N, K, alpha, C.c_void_p(a.data_ptr()), K, C.c_void_p(b.data_ptr()), K, beta,
+                              C.c_void_p(out.data_ptr()), N, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, lib.ds2_last_error()
+        ref = alpha * (a.double() @ b.double().t()) + beta * c0.double()
+        assert rel_l2(out, ref) < 1e-5, (cfg, M, N, K)
