@@ -486,3 +486,40 @@ def test_gemm_f16_tile_configurations_vs_fp64(cfg, monkeypatch):
         assert rc == 0, lib.ds2_last_error()
         ref = alpha * (a.double() @ b.double().t()) + beta * c0.double()
         assert rel_l2(out, ref) < 1e-5, (cfg, M, N, K)
+
+
+@pytest.mark.parametrize("T,B", [(301, 5), (1000, 3)])
+def test_conv_frontend_tensor_core_paths_vs_fp32(T, B):
+    """tensor-core front-end (conv2 forward on tcgen05, TF32) against the FFMA front-end on a ragged batch: several
+    128-position tiles per row, a partially filled last tile, fully masked tiles, BatchNorm batch statistics (running
+    stats) from the fused partial sums; masked frames exactly zero."""
+    g = torch.Generator().manual_seed(T)
+    x = torch.randn(B, 1, 161, T, generator=g)
+    lens = sorted([max(40, T - (T // 4) * i) for i in range(B)], reverse=True)
+    for b, l in enumerate(lens):
+        x[b, :, :, l:] = 0
+    outs = {}
+    for prec in ("fp32", "tf32"):
+        ds.set_precision(prec)
+        model = make_model("gru", True, 8, 1).train()
+        torch.manual_seed(1)
+        sm = model.conv.seq_module
+        with torch.no_grad():
+            for m in (sm[0], sm[3]):
+                m.weight.copy_(torch.randn(m.weight.shape, generator=torch.Generator().manual_seed(5)).cuda() * 0.05)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=torch.Generator().manual_seed(6)).cuda() * 0.1)
+        out_len = model.get_seq_lens(torch.tensor(lens)).cuda()
+        y = ds.ops.ConvFrontend.apply(x.cuda(), out_len, sm[0].weight, sm[0].bias, sm[1].weight, sm[1].bias,
+                                      sm[1].running_mean, sm[1].running_var, sm[3].weight, sm[3].bias, sm[4].weight,
+                                      sm[4].bias, sm[4].running_mean, sm[4].running_var, True, 0.1, 1e-5)
+        torch.cuda.synchronize()
+        outs[prec] = (y.detach().clone(), sm[1].running_mean.clone(), sm[1].running_var.clone(),
+                      sm[4].running_mean.clone(), sm[4].running_var.clone(), out_len.cpu())
+    a, r = outs["tf32"], outs["fp32"]
+    assert rel(a[0], r[0]) < 3e-3 and rel_l2(a[0], r[0]) < 1e-3
+    for i in range(1, 5):
+        assert rel(a[i], r[i]) < 1e-3, i
+    ol = a[5]
+    for b in range(B):
+        if int(ol[b]) < a[0].shape[0]:
+            assert float(a[0][int(ol[b]):, b].abs().max()) == 0.0
