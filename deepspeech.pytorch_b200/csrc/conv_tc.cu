@@ -37,6 +37,40 @@ constexpr int THREADS = 192;
 constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + (TO + 10) * OUT_LD * 4 + 256;
 }  // namespace cv
 
+// Warp-converged TMA issue: every lane executes the instruction stream, one elected lane issues (same reason as
+// mma_*_w in tc_common.cuh: a lone divergent lane pays uniform-register round trips per instruction).
+__device__ __forceinline__ void expect_tx_w(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+      "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(tc::smem_u32(bar)), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_w(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+      ::"r"(tc::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_w(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                              int c3) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}"
+      ::"r"(tc::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_w(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                              int c3, int c4) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n\t}"
+      ::"r"(tc::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3), "r"(c4)
+      : "memory");
+}
+
 struct ConvTcParams {
   CUtensorMap tmA;   // 4-D (32 c, T, R_in, B) channels-last input
   CUtensorMap tmW;   // 3-D (32 c, 352 n, taps) packed tap matrices
@@ -90,48 +124,42 @@ __global__ void __launch_bounds__(cv::THREADS, 1) conv_tc_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int jj = 0; jj < nj; ++jj) {
-        const int j = j_lo + jj;
-        const int r = p.row_mul * d + p.row_off + j * p.row_step;
-        const int wi = p.w_off + j * p.w_step;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full[s], (uint32_t)STAGE_BYTES);
-        uint8_t* st = smem + s * STAGE_BYTES;
-        // A: 128 positions starting at t0-5 (negative / beyond-T coordinates are zero-filled = padding)
-        asm volatile(
-            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-            ::"r"(smem_u32(st)), "l"(reinterpret_cast<uint64_t>(&p.tmA)), "r"(smem_u32(&full[s])), "r"(0),
-              "r"(t0 - 5), "r"(r), "r"(b)
-            : "memory");
-        tma_load_3d(st + A_BYTES, &p.tmW, &full[s], 0, 0, wi);
-        tma_load_3d(st + A_BYTES + W_HALF, &p.tmW, &full[s], 0, NN / 2, wi);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
-      }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int jj = 0; jj < nj; ++jj) {
+      const int j = j_lo + jj;
+      const int r = p.row_mul * d + p.row_off + j * p.row_step;
+      const int wi = p.w_off + j * p.w_step;
+      mbar_wait(&empty[s], ph ^ 1);
+      expect_tx_w(&full[s], (uint32_t)STAGE_BYTES);
+      uint8_t* st = smem + s * STAGE_BYTES;
+      // A: 128 positions starting at t0-5 (negative / beyond-T coordinates are zero-filled = padding)
+      tma_load_4d_w(st, &p.tmA, &full[s], 0, t0 - 5, r, b);
+      tma_load_3d_w(st + A_BYTES, &p.tmW, &full[s], 0, 0, wi);
+      tma_load_3d_w(st + A_BYTES + W_HALF, &p.tmW, &full[s], 0, NN / 2, wi);
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = instr_desc(FMT_TF32, MP, NN / 2);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int jj = 0; jj < nj; ++jj) {
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint64_t ad = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES));
-        const uint64_t b0 = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES));
-        const uint64_t b1 = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES + W_HALF));
+    // the whole warp runs the loop, one elected lane issues (a single divergent lane pays ~76 cycles per MMA
+    // in uniform-register round trips; see tc_common.cuh)
+    const uint32_t idesc = instr_desc(FMT_TF32, MP, NN / 2);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int jj = 0; jj < nj; ++jj) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      const uint64_t ad = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES));
+      const uint64_t b0 = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES));
+      const uint64_t b1 = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES + W_HALF));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          mma_tf32(tmem_base, ad + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), idesc, (jj | k) != 0);
-          mma_tf32(tmem_base + (uint32_t)(NN / 2), ad + (uint64_t)(2 * k), b1 + (uint64_t)(2 * k), idesc, (jj | k) != 0);
-        }
-        mma_commit(&empty[s]);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+      for (int k = 0; k < 4; ++k) {
+        mma_tf32_w(tmem_base, ad + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), idesc, (jj | k) != 0);
+        mma_tf32_w(tmem_base + (uint32_t)(NN / 2), ad + (uint64_t)(2 * k), b1 + (uint64_t)(2 * k), idesc, (jj | k) != 0);
       }
-      mma_commit(accum_bar);
+      mma_commit_w(&empty[s]);
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
+    mma_commit_w(accum_bar);
   } else {
     const int q = warp % 4, e = threadIdx.x - 64;
     const int pl = q * 32 + lane;                     // position inside the tile (TMEM lane)
@@ -287,24 +315,6 @@ struct WgradParams {
 //   box (t0-4, copies 0,1) -> kw 1,0 | (t0, copies 0..3) -> kw 5,4,3,2 | (t0+4, copies 0..3) -> kw 9,8,7,6 | (t0+8, copy 3) -> kw 10
 __constant__ int KW_OF_BLOCK[11] = {1, 0, 5, 4, 3, 2, 9, 8, 7, 6, 10};
 
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(tc::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
-        "r"(c3)
-      : "memory");
-}
-
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(tc::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
-        "r"(c3), "r"(c4)
-      : "memory");
-}
-
 // TMA needs 16-byte aligned box starts in the innermost dimension, so a shift by sh = kw-5 time steps is
 // split into a multiple of 4 (the box coordinate) and s = 0..3 (which delayed copy is read):
 //   a1r[s][row][t'] = a1[row][t'-s]  for t' in [0, T+4)  (0 outside the row; rows padded to T+4 so that the
@@ -360,47 +370,44 @@ __global__ void __launch_bounds__(wg::THREADS, 1) conv2_wgrad_tc_kernel(const __
   }
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int pi = p0; pi < p1; ++pi) {
-        const int b = pi / DS2_CONV2_D, d = pi % DS2_CONV2_D, r = 2 * d + kh - 10;
-        if (r < 0 || r >= DS2_CONV1_D) continue;
-        for (int kt = 0; kt < nkt; ++kt) {
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], (uint32_t)(32 * 128 + cv::NN * 128));
-          uint8_t* st = smem + s * STAGE_BYTES;
-          tma_load_4d(st, &p.tmDz, &full[s], kt * KT, d, 0, b);
-          uint8_t* nb = st + A_BYTES;                      // N blocks of 32 rows x 128 B
-          tma_load_5d(nb, &p.tmS2, &full[s], kt * KT - 4, r, 0, b, 0);
-          tma_load_5d(nb + 2 * 4096, &p.tmS4, &full[s], kt * KT, r, 0, b, 0);
-          tma_load_5d(nb + 6 * 4096, &p.tmS4, &full[s], kt * KT + 4, r, 0, b, 0);
-          tma_load_5d(nb + 10 * 4096, &p.tmS1, &full[s], kt * KT + 8, r, 0, b, 3);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
-        }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int pi = p0; pi < p1; ++pi) {
+      const int b = pi / DS2_CONV2_D, d = pi % DS2_CONV2_D, r = 2 * d + kh - 10;
+      if (r < 0 || r >= DS2_CONV1_D) continue;
+      for (int kt = 0; kt < nkt; ++kt) {
+        mbar_wait(&empty[s], ph ^ 1);
+        expect_tx_w(&full[s], (uint32_t)(32 * 128 + cv::NN * 128));
+        uint8_t* st = smem + s * STAGE_BYTES;
+        tma_load_4d_w(st, &p.tmDz, &full[s], kt * KT, d, 0, b);
+        uint8_t* nb = st + A_BYTES;                      // N blocks of 32 rows x 128 B
+        tma_load_5d_w(nb, &p.tmS2, &full[s], kt * KT - 4, r, 0, b, 0);
+        tma_load_5d_w(nb + 2 * 4096, &p.tmS4, &full[s], kt * KT, r, 0, b, 0);
+        tma_load_5d_w(nb + 6 * 4096, &p.tmS4, &full[s], kt * KT + 4, r, 0, b, 0);
+        tma_load_5d_w(nb + 10 * 4096, &p.tmS1, &full[s], kt * KT + 8, r, 0, b, 3);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = instr_desc(FMT_TF32, 64, cv::NN / 2);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int c = 0; c < nchunks; ++c) {
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint64_t ad = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES));
-        const uint64_t b0 = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES));
-        const uint64_t b1 = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES + cv::W_HALF));
+    // warp-converged issue (one elected lane), as in conv_tc_kernel
+    const uint32_t idesc = instr_desc(FMT_TF32, 64, cv::NN / 2);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      const uint64_t ad = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES));
+      const uint64_t b0 = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES));
+      const uint64_t b1 = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES + cv::W_HALF));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          mma_tf32(tmem_base, ad + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), idesc, (c | k) != 0);
-          mma_tf32(tmem_base + (uint32_t)(cv::NN / 2), ad + (uint64_t)(2 * k), b1 + (uint64_t)(2 * k), idesc, (c | k) != 0);
-        }
-        mma_commit(&empty[s]);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+      for (int k = 0; k < 4; ++k) {
+        mma_tf32_w(tmem_base, ad + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), idesc, (c | k) != 0);
+        mma_tf32_w(tmem_base + (uint32_t)(cv::NN / 2), ad + (uint64_t)(2 * k), b1 + (uint64_t)(2 * k), idesc, (c | k) != 0);
       }
-      mma_commit(accum_bar);
+      mma_commit_w(&empty[s]);
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
+    if (nchunks > 0) mma_commit_w(accum_bar);
   } else if (nchunks > 0) {
     // M = 64 accumulator layout: row m lives in TMEM lane (m % 16) + 32 * (m / 16); valid rows: co = 0..31
     const int q = warp % 4;

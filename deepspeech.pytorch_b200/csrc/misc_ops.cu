@@ -149,20 +149,40 @@ __device__ __forceinline__ float clip_coef(const double* sumsq, float grad_scale
   return coef * grad_scale;
 }
 
+__device__ __forceinline__ void adamw_one(float& pi, float gi, float& mi, float& vi, float s, float lr, float b1,
+                                          float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+  gi *= s;
+  pi *= (1.f - lr * wd);                               // decoupled weight decay
+  mi = b1 * mi + (1.f - b1) * gi;
+  vi = b2 * vi + (1.f - b2) * gi * gi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  pi -= (lr / bc1) * (mi / denom);
+}
+
+// 7 streams of 4 bytes per parameter (read p, g, m, v; write p, m, v): 16-byte accesses, the flat buffers are
+// 16-byte aligned (checked by the caller), the n % 4 tail is done element-wise by the last threads.
 __global__ void adamw_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, float lr, float b1, float b2, float eps, float wd, float bc1,
                              float bc2_sqrt, float grad_scale, float max_norm, const double* __restrict__ sumsq,
-                             float* __restrict__ norm_out) {
+                             float* __restrict__ norm_out, int vec) {
   const float s = clip_coef(sumsq, grad_scale, max_norm, norm_out);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float gi = g[i] * s;
-    float pi = p[i] * (1.f - lr * wd);                 // decoupled weight decay
-    float mi = b1 * m[i] + (1.f - b1) * gi;
-    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = pi - (lr / bc1) * (mi / denom);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = vec ? n / 4 : 0;
+  for (int64_t i = tid; i < n4; i += nthr) {
+    float4 pv = reinterpret_cast<float4*>(p)[i], mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    adamw_one(pv.x, gv.x, mv.x, vv.x, s, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+    adamw_one(pv.y, gv.y, mv.y, vv.y, s, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+    adamw_one(pv.z, gv.z, mv.z, vv.z, s, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+    adamw_one(pv.w, gv.w, mv.w, vv.w, s, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (int64_t i = 4 * n4 + tid; i < n; i += nthr) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    adamw_one(pi, g[i], mi, vi, s, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+    p[i] = pi; m[i] = mi; v[i] = vi;
   }
 }
 
@@ -278,8 +298,10 @@ int ds2_adamw_step(int64_t n, float* p, const float* g, float* m, float* v, floa
   blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
   DS2_LAUNCH(sumsq_kernel, blocks, 256, 0, st, n, g, sumsq);
   float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  const int vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                    reinterpret_cast<uintptr_t>(v)) & 15) == 0;
   DS2_LAUNCH(adamw_kernel, blocks, 256, 0, st, n, p, g, m, v, lr, beta1, beta2, eps, wd, bc1, sqrtf(bc2),
-             grad_scale, max_norm, sumsq, grad_norm_out);
+             grad_scale, max_norm, sumsq, grad_norm_out, vec);
   return DS2_OK;
 }
 
