@@ -288,17 +288,25 @@ int conv_tc_run(const float* in_cl, int B, int T, int R_in, int R_out, const flo
 
 // ---- weight gradient of conv2 on tensor cores ---------------------------------------------------------
 //   dW[co][ci][kh][kw] = sum_{b,d,t} dz2[b,co,d,t] * a1[b,ci,2d+kh-10,t+kw-5]
-// GEMM over time (K = t): A = dz2[b,:,d,t-chunk] (32 co rows, M padded to 64), B rows (kw,ci) =
-// a1[b,ci,r,t-chunk shifted by kw-5] (N = 352), both operands K-major.  The producer thread needs ~110 cycles
-// per TMA instruction, so the eleven shifted 4 KB tiles are fetched with four boxes that span the "shift copy"
-// dimension of a 4-copy tensor (see shift_copies_kernel); the N blocks then sit in the order KW_OF_BLOCK.  A CTA owns one kh and a slice of the (b,d) pairs, accumulates all of them
-// in TMEM and finally adds its 32 x 352 tile into dW with fp32 atomics.
+// GEMM over time (K = t), organised around the INPUT row r = 2d+kh-10: one fetch of the row's eleven shifted tiles
+// (B operand, N = (kw,ci) = 352) serves every vertical tap kh of r's parity, whose dz2 rows d = (r+10-kh)/2 are
+// stacked in M: a CTA owns a group of 4 taps (M = 4 x 32 co = 128) and a slice of the (b, r) pairs, accumulates them
+// all in TMEM (352 columns) and finally adds its 128 x 352 tile into dW with fp32 atomics.  Rows d outside the output
+// are zero-filled by TMA.  (The first version looped over (b, d) for one kh with M = 32 of 64: every input row was
+// fetched once per tap, 19 GB of L2 -> shared-memory traffic per launch = 11 TB/s, the limit; stacking the taps cuts
+// it to 7.6 GB and fills the M = 128 data path.)
+// The producer needs ~110 cycles per TMA instruction, so the eleven shifted 4 KB tiles are fetched with four boxes
+// that span the "shift copy" dimension of a 4-copy tensor (see shift_copies_kernel); the N blocks then sit in the
+// order KW_OF_BLOCK.
 namespace wg {
 constexpr int KT = 32;                               // time steps per K chunk (128 bytes)
-constexpr int A_BYTES = 64 * 128;                    // 64 M rows (32 valid)
+constexpr int KH = 21;                               // vertical taps of conv2
+constexpr int KH_PER = 4;                            // vertical taps stacked in M
+constexpr int GROUPS = 3;                            // tap groups per parity: kh = parity + 2 * (4 * g + i)
+constexpr int A_BYTES = KH_PER * 32 * 128;           // 128 M rows
 constexpr int B_BYTES = cv::NN * 128;                // 352 rows
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 53248
-constexpr int STAGES = 4;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 61440
+constexpr int STAGES = 3;
 constexpr int THREADS = 192;
 constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256;
 }  // namespace wg
@@ -343,11 +351,18 @@ __global__ void __launch_bounds__(wg::THREADS, 1) conv2_wgrad_tc_kernel(const __
   uint64_t* accum_bar = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int kh = blockIdx.x, slice = blockIdx.y;
-  const int pairs = p.B * DS2_CONV2_D;
-  const int per = (pairs + p.slices - 1) / p.slices;
-  const int p0 = slice * per, p1 = min(pairs, p0 + per);
+  const int parity = blockIdx.x / GROUPS, kh0 = parity + 2 * KH_PER * (blockIdx.x % GROUPS);   // taps kh0 + 2 i
+  const int nkh = min(KH_PER, (KH - 1 - kh0) / 2 + 1);
+  const int nr = (DS2_CONV1_D - parity + 1) / 2;        // input rows of this parity: r = 2 r' + parity
+  const int pairs = p.B * nr;
+  const int per = (pairs + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int p0 = blockIdx.y * per, p1 = min(pairs, p0 + per);
   const int nkt = (p.T + KT - 1) / KT;
+  // a row takes part when at least one of the group's taps has its output row d = (r + 10 - kh) / 2 inside [0, 41)
+  auto row_active = [&](int r) {
+    const int d_hi = (r + 10 - kh0) / 2, d_lo = (r + 10 - (kh0 + 2 * (nkh - 1))) / 2;   // same parity: exact
+    return d_hi >= 0 && d_lo < DS2_CONV2_D;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmDz);
@@ -362,24 +377,22 @@ __global__ void __launch_bounds__(wg::THREADS, 1) conv2_wgrad_tc_kernel(const __
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // number of K chunks this CTA will issue (rows outside the input are skipped)
   int nchunks = 0;
-  for (int pi = p0; pi < p1; ++pi) {
-    const int d = pi % DS2_CONV2_D, r = 2 * d + kh - 10;
-    if (r >= 0 && r < DS2_CONV1_D) nchunks += nkt;
-  }
+  for (int pi = p0; pi < p1; ++pi)
+    if (row_active(2 * (pi % nr) + parity)) nchunks += nkt;
 
   if (warp == 0) {
     int s = 0;
     uint32_t ph = 0;
     for (int pi = p0; pi < p1; ++pi) {
-      const int b = pi / DS2_CONV2_D, d = pi % DS2_CONV2_D, r = 2 * d + kh - 10;
-      if (r < 0 || r >= DS2_CONV1_D) continue;
+      const int b = pi / nr, r = 2 * (pi % nr) + parity;
+      if (!row_active(r)) continue;
       for (int kt = 0; kt < nkt; ++kt) {
         mbar_wait(&empty[s], ph ^ 1);
-        expect_tx_w(&full[s], (uint32_t)(32 * 128 + cv::NN * 128));
+        expect_tx_w(&full[s], (uint32_t)(nkh * 32 * 128 + cv::NN * 128));
         uint8_t* st = smem + s * STAGE_BYTES;
-        tma_load_4d_w(st, &p.tmDz, &full[s], kt * KT, d, 0, b);
+        for (int i = 0; i < nkh; ++i)    // dz2 rows of the stacked taps; d outside [0, 41) arrives as zeros
+          tma_load_4d_w(st + i * 4096, &p.tmDz, &full[s], kt * KT, (r + 10 - kh0) / 2 - i, 0, b);
         uint8_t* nb = st + A_BYTES;                      // N blocks of 32 rows x 128 B
         tma_load_5d_w(nb, &p.tmS2, &full[s], kt * KT - 4, r, 0, b, 0);
         tma_load_5d_w(nb + 2 * 4096, &p.tmS4, &full[s], kt * KT, r, 0, b, 0);
@@ -390,7 +403,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) conv2_wgrad_tc_kernel(const __
     }
   } else if (warp == 1) {
     // warp-converged issue (one elected lane), as in conv_tc_kernel
-    const uint32_t idesc = instr_desc(FMT_TF32, 64, cv::NN / 2);
+    const uint32_t idesc = instr_desc(FMT_TF32, 128, cv::NN / 2);
     int s = 0;
     uint32_t ph = 0;
     for (int c = 0; c < nchunks; ++c) {
@@ -409,21 +422,19 @@ __global__ void __launch_bounds__(wg::THREADS, 1) conv2_wgrad_tc_kernel(const __
     }
     if (nchunks > 0) mma_commit_w(accum_bar);
   } else if (nchunks > 0) {
-    // M = 64 accumulator layout: row m lives in TMEM lane (m % 16) + 32 * (m / 16); valid rows: co = 0..31
+    // M = 128: row m = 32 i + co lives in TMEM lane m; warp quadrant q reads tap i = q, lane = co
     const int q = warp % 4;
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    if (q < 2) {
-      const int co = q * 16 + lane;
+    if (q < nkh) {      // rows of taps beyond the last one were never loaded
+      const int kh = kh0 + 2 * q, co = lane;
       for (int blk = 0; blk < cv::KW; ++blk) {
         const int kw = KW_OF_BLOCK[blk];
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * 32), v);
-        if (lane < 16) {
 #pragma unroll
-          for (int ci = 0; ci < 32; ++ci)
-            atomicAdd(&p.dw2[(((size_t)co * 32 + ci) * 21 + kh) * 11 + kw], v[ci]);
-        }
+        for (int ci = 0; ci < 32; ++ci)
+          atomicAdd(&p.dw2[(((size_t)co * 32 + ci) * KH + kh) * 11 + kw], v[ci]);
       }
     }
   }
@@ -461,13 +472,13 @@ int conv2_wgrad_tc(const float* dz2, const float* a1, float* a1_shifted /* 4*B*3
     int rc = make_tmap_4d_f32(&p.tmDz, dz2, dims, str, box);
     if (rc) return rc;
   }
-  p.B = B; p.T = T; p.slices = 7; p.dw2 = dw2;
+  p.B = B; p.T = T; p.slices = 24; p.dw2 = dw2;   // 2 parities x 3 tap groups x 24 slices = 144 CTAs
   static DeviceOnce attr_once;
   if (attr_once.first()) {
     DS2_CHECK_CUDA(cudaFuncSetAttribute(conv2_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
     attr_once.done();
   }
-  DS2_LAUNCH(conv2_wgrad_tc_kernel, dim3(21, p.slices), wg::THREADS, wg::SMEM_BYTES, st, p);
+  DS2_LAUNCH(conv2_wgrad_tc_kernel, dim3(2 * wg::GROUPS, p.slices), wg::THREADS, wg::SMEM_BYTES, st, p);
   return DS2_OK;
 }
 

@@ -490,28 +490,33 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
       rc = f32_to_f16_transpose(TB, (int)DGH, R.gates, DGH, dG16, DGH, dG16T, (size_t)TB, scale, st);
       if (rc) return rc;
     }
-    rc = f32_to_f16_transpose(TB, In, xin, (size_t)In, nullptr, 0, x16T, (size_t)TB, nullptr, st);
-    if (rc) return rc;
     for (int dir = 0; dir < D; ++dir) {
-      rc = f32_to_f16_transpose(TB, H, R.hseq + (size_t)dir * TB * H, (size_t)H, nullptr, 0, h16T + (size_t)dir * H * TB,
-                                (size_t)TB, nullptr, st);
-      if (rc) return rc;
-      if (gru && !f16_done) {
-        rc = f32_to_f16_transpose(TB, H, R.aux + (size_t)dir * TB * H, (size_t)H, nullptr, 0,
-                                  aux16T + (size_t)dir * H * TB, (size_t)TB, scale, st);
-        if (rc) return rc;
-      }
       rc = f32_to_f16_transpose(GH, In, w_ih[dir], (size_t)In, nullptr, 0, w16T + (size_t)dir * GH, DGH, nullptr, st);
       if (rc) return rc;
     }
   }
   // weight-gradient GEMMs: nobody needs dW_ih / dW_hh before the optimizer, so (precision-16 path, caller opted in)
-  // they go to the side stream, ordered after the sweep and the operand copies, and overlap the next layer's sweep
+  // they go to the side stream together with the operand copies only they read (x16T, h16T), ordered after the sweep,
+  // and overlap the next layer's sweep.  The side stream then reads x / reserve until ds2_join_side_stream.
   cudaStream_t gst = st;
   if (f16 && side && d->deferred_dw) {
     rc = side_fork(st, side);
     if (rc) return rc;
     gst = side;
+  }
+  if (f16) {
+    rc = f32_to_f16_transpose(TB, In, xin, (size_t)In, nullptr, 0, x16T, (size_t)TB, nullptr, gst);
+    if (rc) return rc;
+    for (int dir = 0; dir < D; ++dir) {
+      rc = f32_to_f16_transpose(TB, H, R.hseq + (size_t)dir * TB * H, (size_t)H, nullptr, 0, h16T + (size_t)dir * H * TB,
+                                (size_t)TB, nullptr, gst);
+      if (rc) return rc;
+      if (gru && !f16_done) {
+        rc = f32_to_f16_transpose(TB, H, R.aux + (size_t)dir * TB * H, (size_t)H, nullptr, 0,
+                                  aux16T + (size_t)dir * H * TB, (size_t)TB, scale, gst);
+        if (rc) return rc;
+      }
+    }
   }
   bool dx_done = false;
   if (f16 && dx) {   // dX = dG (TB x D*GH) . [W_ih fwd ; W_ih rev] : one K = D*G*H GEMM for both directions

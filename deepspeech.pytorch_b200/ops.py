@@ -276,6 +276,11 @@ class RnnLayer(torch.autograd.Function):
                                     ptr_array(grads[0::4]), ptr_array(grads[1::4]), ptr_array(grads[2::4]),
                                     ptr_array(grads[3::4]), ptr(ws), ws.numel(), _stream()), "ds2_rnn_layer_bwd")
         assert len(grads) == 4 * D
+        if desc.deferred_dw:
+            # the side stream still reads the layer input and the saved sequences (operand copies of the deferred
+            # weight-gradient GEMMs): keep the caching allocator from handing them out before that work has run
+            for t in (x, reserve):
+                t.record_stream(_side["stream"])
         return (dx, None, None, None, None, None, None, rdg, rdb, None, None, None, None, *rgrads)
 
 

@@ -72,7 +72,9 @@ int64_t ds2_fallback_count(int reset);
  * after the layer's sweep and operand copies; they then run in the shadow of the next layer's latency-bound sweep.
  * The caller (a) alternates between two workspaces for consecutive layers (the library orders the reuse of a
  * workspace after the side work that read it), (b) calls ds2_join_side_stream(stream) before anything on `stream`
- * (or any other stream ordered after it) reads those gradients.  NULL disables (default).                      */
+ * (or any other stream ordered after it) reads those gradients, (c) keeps `x` and `reserve` of that call valid until
+ * the side stream has passed this point (the transposed fp16 copies of the layer input and of the hidden sequence are
+ * made on the side stream too).  NULL disables (default).                                                        */
 int ds2_set_side_stream(void* stream);
 int ds2_join_side_stream(void* stream);
 
