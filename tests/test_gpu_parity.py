@@ -488,11 +488,12 @@ def test_gemm_f16_tile_configurations_vs_fp64(cfg, monkeypatch):
         assert rel_l2(out, ref) < 1e-5, (cfg, M, N, K)
 
 
-@pytest.mark.parametrize("T,B", [(301, 5), (1000, 3)])
+@pytest.mark.parametrize("T,B", [(301, 5), (1000, 3), (301, 4), (640, 6)])
 def test_conv_frontend_tensor_core_paths_vs_fp32(T, B):
-    """tensor-core front-end (conv2 forward on tcgen05, TF32) against the FFMA front-end on a ragged batch: several
-    128-position tiles per row, a partially filled last tile, fully masked tiles, BatchNorm batch statistics (running
-    stats) from the fused partial sums; masked frames exactly zero."""
+    """tensor-core front-end (conv2 forward / data gradient / weight gradient on tcgen05, TF32) against the FFMA
+    front-end on a ragged batch: several 128-position tiles per row, a partially filled last tile, fully masked tiles,
+    BatchNorm batch statistics (running stats) from the fused partial sums; masked frames exactly zero.  Odd batches
+    run one CTA per tile, even ones the 2-CTA clusters that share the tap matrices by multicast."""
     g = torch.Generator().manual_seed(T)
     x = torch.randn(B, 1, 161, T, generator=g)
     lens = sorted([max(40, T - (T // 4) * i) for i in range(B)], reverse=True)
@@ -512,13 +513,22 @@ def test_conv_frontend_tensor_core_paths_vs_fp32(T, B):
         y = ds.ops.ConvFrontend.apply(x.cuda(), out_len, sm[0].weight, sm[0].bias, sm[1].weight, sm[1].bias,
                                       sm[1].running_mean, sm[1].running_var, sm[3].weight, sm[3].bias, sm[4].weight,
                                       sm[4].bias, sm[4].running_mean, sm[4].running_var, True, 0.1, 1e-5)
+        dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(9)).cuda()
+        for m in (sm[0], sm[1], sm[3], sm[4]):
+            m.weight.grad = m.bias.grad = None
+        (y * dy).sum().backward()
         torch.cuda.synchronize()
         outs[prec] = (y.detach().clone(), sm[1].running_mean.clone(), sm[1].running_var.clone(),
-                      sm[4].running_mean.clone(), sm[4].running_var.clone(), out_len.cpu())
+                      sm[4].running_mean.clone(), sm[4].running_var.clone(), out_len.cpu(),
+                      [m.weight.grad.clone() for m in (sm[0], sm[1], sm[3], sm[4])])
     a, r = outs["tf32"], outs["fp32"]
     assert rel(a[0], r[0]) < 3e-3 and rel_l2(a[0], r[0]) < 1e-3
     for i in range(1, 5):
         assert rel(a[i], r[i]) < 1e-3, i
+    # gradients: conv1 weight (through the conv2 data gradient), BN1, conv2 weight, BN2.  The Hardtanh clips are not
+    # smooth, so a TF32 forward deviation flips a few clip masks: percent-level bound, not 1e-3
+    for i, (ga, gr) in enumerate(zip(a[6], r[6])):
+        assert torch.isfinite(ga).all() and rel_l2(ga, gr) < 3e-2, (i, rel_l2(ga, gr))
     ol = a[5]
     for b in range(B):
         if int(ol[b]) < a[0].shape[0]:
