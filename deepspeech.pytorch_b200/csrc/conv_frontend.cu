@@ -449,6 +449,7 @@ int conv_tc_run(const float* in_cl, int B, int T, int R_in, int R_out, const flo
 int nchw_to_cl(int B, int R, int T, const float* in, float* out, cudaStream_t st);
 int pack_conv2_tc(const float* w2, float* wn_fwd, float* wd_bwd, cudaStream_t st);
 int conv2_wgrad_tc(const float* dz2, const float* a1, float* a1_shifted, int B, int T, float* dw2, cudaStream_t st);
+int conv1_wgrad_tc(const float* dz1, const float* x, float* xs, int B, int T, int Tp, float* dw1, cudaStream_t st);
 
 struct ConvWs {
   float *wpk1, *wpk2, *wTe, *wTo, *du2, *da1;
@@ -593,7 +594,15 @@ int ds2_conv_frontend_bwd(int B, int T, const float* x, const int32_t* out_len, 
   DS2_LAUNCH(bn_bwd_params2d_kernel, 1, 32, 0, st, s1, dg1, dbe1);
   DS2_LAUNCH(bn_bwd_apply_kernel, dim3(cdiv(D1 * Tp, 256), CO, B), 256, 0, st, B, D1, Tp, 1.0 / ((double)B * D1 * Tp),
              z1, stats, g1, out_len, s1, W.da1, db1);
-  DS2_LAUNCH(conv1_dw_kernel, dim3(3, B, C1_DSPLIT), 128, 0, st, B, T, Tp, W.da1, x, dw1);
+  {
+    // conv1 weight gradient on tcgen05 (reuses the conv2 weight gradient's staging buffer, which is free by now)
+    int wrc = 1;
+    if (tensor_core_mode() && !getenv("DS2_NO_CONV_TC") && !getenv("DS2_NO_CONV1_TC_WGRAD")) {
+      wrc = conv1_wgrad_tc(W.da1, x, W.shifted, B, T, Tp, dw1, st);
+      if (wrc < 0) return wrc;
+    }
+    if (wrc == 1) DS2_LAUNCH(conv1_dw_kernel, dim3(3, B, C1_DSPLIT), 128, 0, st, B, T, Tp, W.da1, x, dw1);
+  }
   return DS2_OK;
 }
 

@@ -482,6 +482,177 @@ int conv2_wgrad_tc(const float* dz2, const float* a1, float* a1_shifted /* 4*B*3
   return DS2_OK;
 }
 
+// ---- weight gradient of conv1 (1 -> 32 channels, 41 x 11 taps, stride 2 x 2) on tensor cores -----------------
+//   dW1[co][kh][kw] = sum_{b,d,t} dz1[b,co,d,t] * x[b, 2d+kh-20, 2t+kw-5]
+// GEMM over time (K = t) between four stacked output rows (M = (co, i): dz1 rows d0..d0+3) and eight stacked input
+// rows (N = (tap column, j): x rows r0..r0+7, each in its twelve time-shifted / de-interleaved variants), so that one
+// MMA chunk covers 32 (i, j) pairs = 14 vertical taps kh = 8c + j - 2i of class c (r0 = 2 d0 - 20 + 8c; six classes
+// cover kh = 0..40).  The stride-2 time axis is de-interleaved (q = parity of 2t+kw-5) and, because TMA boxes start
+// on 16-byte boundaries, kept in four delayed copies s (conv1_shift_copies_kernel):
+//   xs[s][q][b][r][u'] = x[b][r][2(u'-s)+q],   x[2t+kw-5] = xs[s][q][t + m + s]  with kw-5 = 2m+q, (m+s) % 4 == 0
+// Two boxes per chunk fetch all of them: (t0; s=0..3, q=0..1) and (t0+4; s=2..3, q=0..1); shared-memory N row
+// n = (2s+q) * 8 + j  resp.  64 + (2(s-2)+q) * 8 + j, whose tap column is KW1_OF_GROUP[n / 8].  Rows outside the
+// image / the output arrive as TMA zero fill.  37 GFLOP: 1.38 ms on FFMA (shared-memory bound) before.
+namespace w1 {
+constexpr int KT = 32;                               // time steps per K chunk (128 bytes)
+constexpr int DI = 4, RJ = 8;                        // stacked output rows / input rows
+constexpr int NROWS = 12 * RJ;                       // 96 N rows (11 tap columns + 1 unused variant)
+constexpr int CLASSES = 6;
+constexpr int A_BYTES = 32 * DI * 128;               // 128 M rows
+constexpr int B_BYTES = NROWS * 128;                 // 12 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 28672
+constexpr int STAGES = 6;
+constexpr int THREADS = 192;
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256;
+}  // namespace w1
+__constant__ int KW1_OF_GROUP[12] = {5, 6, 3, 4, 1, 2, -1, 0, 9, 10, 7, 8};
+
+struct Wgrad1Params {
+  CUtensorMap tmDz;   // 4-D (T', 81, 32 co, B), box (32, 4, 32, 1)
+  CUtensorMap tmX8;   // 5-D (T'+4, 161, B, 2 q, 4 s), box (32, 8, 1, 2, 4)
+  CUtensorMap tmX4;   // same tensor, box (32, 8, 1, 2, 2)
+  int B, Tp;
+  float* dw1;
+};
+
+__global__ void conv1_shift_copies_kernel(int B, int T, int Tp, const float* __restrict__ x, float* __restrict__ xs) {
+  const int U = Tp + 4;
+  const size_t rows = (size_t)B * DS2_NUM_FREQ, n = rows * U, total = 8 * n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int up = (int)(i % U);
+    const size_t row = (i / U) % rows;
+    const int sq = (int)(i / n), q = sq & 1, sft = sq >> 1;
+    const int u = up - sft, tx = 2 * u + q;
+    xs[i] = (u >= 0 && tx < T) ? x[row * T + tx] : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(w1::THREADS, 1) conv1_wgrad_tc_kernel(const __grid_constant__ Wgrad1Params p) {
+  using namespace w1;
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum_bar = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int cls = blockIdx.x;
+  const int ndb = (DS2_CONV1_D + DI - 1) / DI;              // 21 blocks of output rows
+  const int pairs = p.B * ndb;
+  const int per = (pairs + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int p0 = blockIdx.y * per, p1 = min(pairs, p0 + per);
+  const int nkt = (p.Tp + KT - 1) / KT;
+  auto block_active = [&](int db) {   // some input row of the block lies inside the image
+    const int r0 = 2 * DI * db - 20 + RJ * cls;
+    return r0 + RJ - 1 >= 0 && r0 < DS2_NUM_FREQ;
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmDz);
+    tma_prefetch_desc(&p.tmX8);
+    tma_prefetch_desc(&p.tmX4);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int nchunks = 0;
+  for (int pi = p0; pi < p1; ++pi)
+    if (block_active(pi % ndb)) nchunks += nkt;
+
+  if (warp == 0) {
+    int s = 0;
+    uint32_t ph = 0;
+    for (int pi = p0; pi < p1; ++pi) {
+      const int b = pi / ndb, db = pi % ndb;
+      if (!block_active(db)) continue;
+      const int d0 = DI * db, r0 = 2 * d0 - 20 + RJ * cls;
+      for (int kt = 0; kt < nkt; ++kt) {
+        mbar_wait(&empty[s], ph ^ 1);
+        expect_tx_w(&full[s], (uint32_t)STAGE_BYTES);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        tma_load_4d_w(st, &p.tmDz, &full[s], kt * KT, d0, 0, b);                       // rows m = co * 4 + i
+        tma_load_5d_w(st + A_BYTES, &p.tmX8, &full[s], kt * KT, r0, b, 0, 0);           // 64 rows
+        tma_load_5d_w(st + A_BYTES + 64 * 128, &p.tmX4, &full[s], kt * KT + 4, r0, b, 0, 2);   // 32 rows
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = instr_desc(FMT_TF32, 128, NROWS);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      const uint64_t ad = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES));
+      const uint64_t bd = smem_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_BYTES));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mma_tf32_w(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (c | k) != 0);
+      mma_commit_w(&empty[s]);
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+    }
+    if (nchunks > 0) mma_commit_w(accum_bar);
+  } else if (nchunks > 0) {
+    // accumulator row m = co * 4 + i sits in TMEM lane m
+    const int q = warp % 4, m = q * 32 + lane, co = m / DI, i = m % DI;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    for (int blk = 0; blk < NROWS / 32; ++blk) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * 32), v);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int n = blk * 32 + c, kw = KW1_OF_GROUP[n / RJ], kh = RJ * cls + (n % RJ) - 2 * i;
+        if (kw >= 0 && kh >= 0 && kh < 41) atomicAdd(&p.dw1[((size_t)co * 41 + kh) * 11 + kw], v[c]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<128>(tmem_base);
+}
+
+// dz1: (B,32,81,T') gradient of the conv1 output (after the BN1 / Hardtanh backward); x: (B,1,161,T); dw1 (32,1,41,11)
+// must be zeroed.  xs: 8 * B * 161 * (T'+4) floats.  Returns 1 when the shape is not eligible (T' % 4 != 0).
+int conv1_wgrad_tc(const float* dz1, const float* x, float* xs, int B, int T, int Tp, float* dw1, cudaStream_t st) {
+  if (Tp % 4 != 0) return 1;
+  Wgrad1Params p{};
+  const unsigned long long U = (unsigned long long)Tp + 4, F = DS2_NUM_FREQ;
+  DS2_LAUNCH(conv1_shift_copies_kernel, 148 * 8, 256, 0, st, B, T, Tp, x, xs);
+  {
+    unsigned long long dims[5] = {U, F, (unsigned long long)B, 2ull, 4ull};
+    unsigned long long str[4] = {U * 4, F * U * 4, (unsigned long long)B * F * U * 4, 2ull * B * F * U * 4};
+    unsigned int box[5] = {32u, (unsigned int)w1::RJ, 1u, 2u, 4u};
+    int rc = make_tmap_nd_f32(&p.tmX8, xs, 5, dims, str, box);
+    if (rc) return rc;
+    box[4] = 2u;
+    rc = make_tmap_nd_f32(&p.tmX4, xs, 5, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    unsigned long long dims[4] = {(unsigned long long)Tp, (unsigned long long)DS2_CONV1_D, 32ull, (unsigned long long)B};
+    unsigned long long str[3] = {(unsigned long long)Tp * 4, (unsigned long long)DS2_CONV1_D * Tp * 4,
+                                 32ull * DS2_CONV1_D * Tp * 4};
+    unsigned int box[4] = {32u, (unsigned int)w1::DI, 32u, 1u};
+    int rc = make_tmap_4d_f32(&p.tmDz, dz1, dims, str, box);
+    if (rc) return rc;
+  }
+  p.B = B; p.Tp = Tp; p.dw1 = dw1;
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
+    DS2_CHECK_CUDA(cudaFuncSetAttribute(conv1_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, w1::SMEM_BYTES));
+    attr_once.done();
+  }
+  DS2_LAUNCH(conv1_wgrad_tc_kernel, dim3(w1::CLASSES, 24), w1::THREADS, w1::SMEM_BYTES, st, p);
+  return DS2_OK;
+}
+
 }  // namespace ds2
 
 // tensor-map helper lives next to the other encoders (needs the driver entry point loaded in gemm_tc.cu)

@@ -77,3 +77,30 @@ def test_conv2_wgrad_tap_order_matches_the_box_plan():
         coord, copy = plan[blk]
         sh = kw - 5                               # a1[t + sh] = copy[t + sh + copy]  (copy delayed by `copy` steps)
         assert coord == sh + copy and coord % 4 == 0
+
+
+# ---- conv1 weight gradient: de-interleaved, delayed copies of the stride-2 time axis (conv_tc.cu: KW1_OF_GROUP) ----
+def test_conv1_wgrad_tap_columns_match_the_box_plan():
+    """xs[s][q][u'] = x[2 (u' - s) + q]; box 1 at coordinate t0 spans s = 0..3, q = 0..1, box 2 at t0 + 4 spans
+    s = 2..3: group g of 8 shared-memory rows must hold x[2 t + kw - 5] for kw = KW1_OF_GROUP[g], and the six classes
+    of (4 output rows) x (8 input rows) must reach every vertical tap exactly once per output row."""
+    src = (SRC / "conv_tc.cu").read_text()
+    m = re.search(r"KW1_OF_GROUP\[12\] = \{([-0-9, ]+)\}", src)
+    table = [int(v) for v in m.group(1).split(",")]
+    groups = [(0, s, q) for s in range(4) for q in range(2)] + [(4, s, q) for s in (2, 3) for q in range(2)]
+    assert len(groups) == len(table) == 12
+    seen = set()
+    for g, (coord, s, q) in enumerate(groups):
+        # row element k of the box is xs[s][q][t0 + coord + k] = x[2 (t0 + coord + k - s) + q]: for output step
+        # t = t0 + k that is x[2 t + 2 (coord - s) + q], i.e. tap column kw = 5 + 2 (coord - s) + q
+        kw = 5 + 2 * (coord - s) + q
+        if 0 <= kw <= 10:
+            assert table[g] == kw
+            seen.add(kw)
+        else:
+            assert table[g] == -1
+    assert seen == set(range(11))
+    # vertical taps: kh = 8 c + j - 2 i for class c, input row j of 8, output row i of 4
+    for i in range(4):
+        hits = sorted(8 * c + j - 2 * i for c in range(6) for j in range(8) if 0 <= 8 * c + j - 2 * i < 41)
+        assert hits == list(range(41))
