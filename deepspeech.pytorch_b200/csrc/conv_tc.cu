@@ -37,21 +37,7 @@ constexpr int THREADS = 192;
 constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + (TO + 10) * OUT_LD * 4 + 256;
 }  // namespace cv
 
-// Warp-converged TMA issue: every lane executes the instruction stream, one elected lane issues (same reason as
-// mma_*_w in tc_common.cuh: a lone divergent lane pays uniform-register round trips per instruction).
-__device__ __forceinline__ void expect_tx_w(uint64_t* bar, uint32_t bytes) {
-  asm volatile(
-      "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
-      "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(tc::smem_u32(bar)), "r"(bytes)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_w(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
-      "@pe cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
-      ::"r"(tc::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
+// Warp-converged TMA issue (see tc_common.cuh): 4-D / 5-D boxes of the conv kernels
 __device__ __forceinline__ void tma_load_4d_w(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
                                               int c3) {
   asm volatile(
@@ -131,7 +117,7 @@ __global__ void __launch_bounds__(cv::THREADS, 1) conv_tc_kernel(const __grid_co
       const int r = p.row_mul * d + p.row_off + j * p.row_step;
       const int wi = p.w_off + j * p.w_step;
       mbar_wait(&empty[s], ph ^ 1);
-      expect_tx_w(&full[s], (uint32_t)STAGE_BYTES);
+      mbar_arrive_expect_tx_w(&full[s], (uint32_t)STAGE_BYTES);
       uint8_t* st = smem + s * STAGE_BYTES;
       // A: 128 positions starting at t0-5 (negative / beyond-T coordinates are zero-filled = padding)
       tma_load_4d_w(st, &p.tmA, &full[s], 0, t0 - 5, r, b);
@@ -389,7 +375,7 @@ __global__ void __launch_bounds__(wg::THREADS, 1) conv2_wgrad_tc_kernel(const __
       if (!row_active(r)) continue;
       for (int kt = 0; kt < nkt; ++kt) {
         mbar_wait(&empty[s], ph ^ 1);
-        expect_tx_w(&full[s], (uint32_t)(nkh * 32 * 128 + cv::NN * 128));
+        mbar_arrive_expect_tx_w(&full[s], (uint32_t)(nkh * 32 * 128 + cv::NN * 128));
         uint8_t* st = smem + s * STAGE_BYTES;
         for (int i = 0; i < nkh; ++i)    // dz2 rows of the stacked taps; d outside [0, 41) arrives as zeros
           tma_load_4d_w(st + i * 4096, &p.tmDz, &full[s], kt * KT, (r + 10 - kh0) / 2 - i, 0, b);
@@ -575,7 +561,7 @@ __global__ void __launch_bounds__(w1::THREADS, 1) conv1_wgrad_tc_kernel(const __
       const int d0 = DI * db, r0 = 2 * d0 - 20 + RJ * cls;
       for (int kt = 0; kt < nkt; ++kt) {
         mbar_wait(&empty[s], ph ^ 1);
-        expect_tx_w(&full[s], (uint32_t)STAGE_BYTES);
+        mbar_arrive_expect_tx_w(&full[s], (uint32_t)STAGE_BYTES);
         uint8_t* st = smem + s * STAGE_BYTES;
         tma_load_4d_w(st, &p.tmDz, &full[s], kt * KT, d0, 0, b);                       // rows m = co * 4 + i
         tma_load_5d_w(st + A_BYTES, &p.tmX8, &full[s], kt * KT, r0, b, 0, 0);           // 64 rows
