@@ -554,12 +554,27 @@ int ds2_conv_frontend_bwd(int B, int T, const float* x, const int32_t* out_len, 
   DS2_LAUNCH(bn_bwd_params2d_kernel, 1, 32, 0, st, s2, dg2, dbe2);
   DS2_LAUNCH(bn_bwd_apply_kernel, dim3(cdiv(D2 * Tp, 256), CO, B), 256, 0, st, B, D2, Tp, 1.0 / ((double)B * D2 * Tp),
              z2, stats + 64, g2, out_len, s2, W.du2, db2);
-  // ---- conv2 gradients
+  // ---- conv2 gradients.  Nobody needs dW2 before the optimizer: with a side stream set the weight gradient runs there,
+  // next to the data gradient and the (elementwise, HBM-bound) BN1 backward of the main stream, and is joined before
+  // the conv1 weight gradient reuses its staging buffer.
+  cudaStream_t side = as_stream(g_side_stream.load());
+  bool forked = false;
   {
     int wrc = 1;
     if (tensor_core_mode() && !getenv("DS2_NO_CONV_TC") && !getenv("DS2_NO_CONV_TC_WGRAD")) {
-      wrc = conv2_wgrad_tc(W.du2, a1, W.shifted, B, Tp, dw2, st);
+      cudaStream_t wst = st;
+      if (side && Tp % 4 == 0) {
+        int frc = side_fork(st, side);
+        if (frc) return frc;
+        wst = side;
+        forked = true;
+      }
+      wrc = conv2_wgrad_tc(W.du2, a1, W.shifted, B, Tp, dw2, wst);
       if (wrc < 0) return wrc;
+      if (forked) {
+        int mrc = side_mark_workspace(ws, side);
+        if (mrc) return mrc;
+      }
     }
     if (wrc == 1) DS2_LAUNCH(conv2_dw_kernel, dim3(21, B), 256, 0, st, B, Tp, W.du2, a1, dw2);
   }
@@ -594,6 +609,10 @@ int ds2_conv_frontend_bwd(int B, int T, const float* x, const int32_t* out_len, 
   DS2_LAUNCH(bn_bwd_params2d_kernel, 1, 32, 0, st, s1, dg1, dbe1);
   DS2_LAUNCH(bn_bwd_apply_kernel, dim3(cdiv(D1 * Tp, 256), CO, B), 256, 0, st, B, D1, Tp, 1.0 / ((double)B * D1 * Tp),
              z1, stats, g1, out_len, s1, W.da1, db1);
+  if (forked) {   // dW2 done (and its staging buffer free) before this call returns
+    int jrc = side_wait_for_workspace(ws, st);
+    if (jrc) return jrc;
+  }
   {
     // conv1 weight gradient on tcgen05 (reuses the conv2 weight gradient's staging buffer, which is free by now)
     int wrc = 1;
