@@ -33,6 +33,16 @@ struct SeqArgs {
   void* f16_auxT;
   const float* f16_scale;
   int* f16_done;
+  // bwd, optional: fp16 copy of the transposed recurrent matrix (H, G*H) made by the forward pass of the same step.
+  // The fp16-resident sweep takes it as it is; then w_hh[] points at buffers that are only filled (fp32 transposes)
+  // when a path that needs them calls materialize_w_hh().
+  const void* w_hhT16[2];
+  int (*fill_w_hh)(void* ctx, void* stream);
+  void* fill_w_hh_ctx;
 };
+
+inline int materialize_w_hh(const SeqArgs& a, void* stream) {
+  return a.fill_w_hh ? a.fill_w_hh(a.fill_w_hh_ctx, stream) : 0;
+}
 
 }  // namespace ds2

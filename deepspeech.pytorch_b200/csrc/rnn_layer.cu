@@ -11,6 +11,9 @@
 //                           GRU W_hn h + b_hn; absent for tanh) | bn mean,invstd (2*In)
 #include <cuda_fp16.h>
 
+#include <mutex>
+#include <unordered_set>
+
 #include "common.cuh"
 #include "rnn_cells.cuh"
 #include "rnn_common.cuh"
@@ -229,6 +232,7 @@ static inline int num_gates(int rnn) { return rnn == DS2_RNN_LSTM ? 4 : (rnn == 
 
 struct Reserve {
   float *gates, *hseq, *aux, *bnstats;
+  __half* wT16;   // (D, H, G*H) fp16 W_hh^T, written by a tensor-core-mode training forward for the backward sweep
   size_t total;
 };
 static Reserve carve_reserve(const ds2_rnn_desc* d, float* base) {
@@ -240,8 +244,40 @@ static Reserve carve_reserve(const ds2_rnn_desc* d, float* base) {
   r.hseq = base + off; off += D * TB * d->H;
   if (d->rnn_type != DS2_RNN_TANH) { r.aux = base + off; off += D * TB * d->H; } else r.aux = nullptr;
   r.bnstats = base + off; off += 2 * (size_t)d->In;
+  off = (off + 3) & ~(size_t)3;                           // 16-byte aligned (TMA source)
+  r.wT16 = reinterpret_cast<__half*>(base + off); off += (D * G * d->H * d->H + 1) / 2;
   r.total = off;
   return r;
+}
+
+// Which reserve buffers hold a valid fp16 W_hh^T (the forward pass that wrote it registers the pointer, the backward
+// pass that consumes the reserve removes it): a backward without the copy simply converts the weights itself.
+static std::mutex g_wT16_mu;
+static std::unordered_set<const void*> g_wT16_valid;
+static void wT16_set(const void* reserve, bool valid) {
+  std::lock_guard<std::mutex> lk(g_wT16_mu);
+  if (valid) g_wT16_valid.insert(reserve); else g_wT16_valid.erase(reserve);
+}
+static bool wT16_take(const void* reserve) {
+  std::lock_guard<std::mutex> lk(g_wT16_mu);
+  return g_wT16_valid.erase(reserve) > 0;
+}
+
+// lazily materialised fp32 W_hh^T of the backward pass (SeqArgs::fill_w_hh)
+struct FillWhh {
+  int GH, H, D, done;
+  const float* const* w_hh;
+  float* wT[2];
+};
+static int fill_w_hh_cb(void* ctx, void* stream) {
+  FillWhh* f = static_cast<FillWhh*>(ctx);
+  if (f->done) return DS2_OK;
+  for (int dir = 0; dir < f->D; ++dir) {
+    int rc = transpose(f->GH, f->H, f->w_hh[dir], f->wT[dir], static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+  }
+  f->done = 1;
+  return DS2_OK;
 }
 
 // tcgen05 persistent sweeps (rnn_persistent_tc.cu).  Return 1 when the shape is not eligible.
@@ -372,6 +408,28 @@ int ds2_rnn_layer_fwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
     if (rc == 1) rc = sweep_fwd(d->rnn_type, a, st);
     if (rc) return rc;
   }
+  // fp16 W_hh^T for the backward sweep of this step (the weights cannot change in between): one pass here instead of a
+  // transpose + a conversion on the backward critical path; on the side stream when there is one
+  wT16_set(reserve, false);
+  if (d->training && tensor_core_mode() && H % 8 == 0) {
+    cudaStream_t side = as_stream(g_side_stream.load());
+    cudaStream_t cst = st;
+    if (side) {
+      rc = side_fork(st, side);
+      if (rc) return rc;
+      cst = side;
+    }
+    for (int dir = 0; dir < D; ++dir) {
+      rc = f32_to_f16_transpose(GH, H, w_hh[dir], (size_t)H, nullptr, 0, R.wT16 + (size_t)dir * H * GH, (size_t)GH,
+                                nullptr, cst);
+      if (rc) return rc;
+    }
+    if (side) {
+      rc = side_mark_workspace(reserve, side);
+      if (rc) return rc;
+    }
+    wT16_set(reserve, true);
+  }
   size_t n = (size_t)TB * H;
   int blocks = (int)((n + 1023) / 1024);
   blocks = blocks > 148 * 16 ? 148 * 16 : blocks;
@@ -414,8 +472,17 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
   void* gws = ar.base + ar.off;
   size_t gws_bytes = ar.cap - ar.off;
 
-  for (int dir = 0; dir < D; ++dir) {
-    rc = transpose(GH, H, w_hh[dir], wT[dir], st);
+  // W_hh^T: fp16 copy from the forward pass when there is one (the fp32 transposes are then made only if a path that
+  // streams fp32 weights is taken), otherwise transposed here
+  FillWhh fill{GH, H, D, 0, w_hh, {wT[0], wT[1]}};
+  const bool have_wT16 = tensor_core_mode() && wT16_take(reserve);
+  if (have_wT16) {
+    if (side) {   // written on the side stream by the forward pass
+      rc = side_wait_for_workspace(reserve, st);
+      if (rc) return rc;
+    }
+  } else {
+    rc = fill_w_hh_cb(&fill, st);
     if (rc) return rc;
   }
   DS2_CHECK_CUDA(cudaMemsetAsync(carry, 0, sizeof(float) * (size_t)D * B * H, st));
@@ -424,6 +491,9 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
   a.gates = R.gates; a.hseq = R.hseq; a.aux = R.aux;
   for (int dir = 0; dir < D; ++dir) { a.w_hh[dir] = wT[dir]; a.b_ih[dir] = b_ih[dir]; a.b_hh[dir] = b_hh[dir]; }
   a.dy = dy; a.carry = carry; a.training = 1;
+  a.fill_w_hh = fill_w_hh_cb; a.fill_w_hh_ctx = &fill;
+  if (have_wT16)
+    for (int dir = 0; dir < D; ++dir) a.w_hhT16[dir] = R.wT16 + (size_t)dir * H * GH;
   // bias gradients are column sums of the gate gradients: the tensor-core sweep can accumulate them on the fly
   int dbias_done = 0;
   const bool gru_l = d->rnn_type == DS2_RNN_GRU;
@@ -468,7 +538,11 @@ int ds2_rnn_layer_bwd(const ds2_rnn_desc* d, const float* x, const int32_t* len,
       rc = rnn_sweep_bwd_tc(d->rnn_type, a, gws, gws_bytes, st);
       if (rc == 1) note_fallback("backward sweep", d->rnn_type, T, B, H, D);
     }
-    if (rc == 1) rc = sweep_bwd(d->rnn_type, a, st);
+    if (rc == 1) {
+      rc = fill_w_hh_cb(&fill, st);
+      if (rc) return rc;
+      rc = sweep_bwd(d->rnn_type, a, st);
+    }
     if (rc) return rc;
   }
 

@@ -2306,9 +2306,18 @@ static int launch_bwd_splitk_resident(const SeqArgs& a, void* ws, size_t ws_byte
   }
   DS2_CHECK_CUDA(cudaMemsetAsync(ws, 0, 4096 + align_up((size_t)a.D * (a.T + 1) * 4, 256), st));
   const size_t wn = (size_t)a.H * GH;
+  const bool cached = a.w_hhT16[0] && (a.D == 1 || a.w_hhT16[1]);   // fp16 W_hh^T left by the forward pass
+  if (!cached) {
+    int rc = materialize_w_hh(a, st);
+    if (rc) return rc;
+  }
   for (int d = 0; d < a.D; ++d) {
-    DS2_LAUNCH(f32_to_f16_kernel, 148 * 4, 256, 0, st, wn, a.w_hh[d], wT16 + (size_t)d * wn);
-    int rc = make_tmap_f16(&p.tmW[d], wT16 + (size_t)d * wn, 2, GH, a.H, 1, (size_t)GH, 0, 64, UM, 1);
+    const __half* wsrc = static_cast<const __half*>(a.w_hhT16[d]);
+    if (!cached) {
+      DS2_LAUNCH(f32_to_f16_kernel, 148 * 4, 256, 0, st, wn, a.w_hh[d], wT16 + (size_t)d * wn);
+      wsrc = wT16 + (size_t)d * wn;
+    }
+    int rc = make_tmap_f16(&p.tmW[d], wsrc, 2, GH, a.H, 1, (size_t)GH, 0, 64, UM, 1);
     if (rc) return rc;
     rc = make_tmap_f16(&p.tmV[d], p.dg16, 2, a.D * GH, a.T * a.B, 1, (size_t)a.D * GH, 0, 64, a.B, 1);
     if (rc) return rc;
@@ -2360,6 +2369,7 @@ static int launch_bwd_splitk(const SeqArgs& a, void* ws, size_t ws_bytes, cudaSt
   }
   constexpr int UM = UT * CL;
   if (a.H % UM != 0 || (GH / CL) % BK != 0 || GH % CL != 0) return 1;
+  { int mrc = materialize_w_hh(a, st); if (mrc) return mrc; }   // this kernel streams the fp32 W_hh^T
   if (CL == 8 && ((a.B + 7) / 8 * 8) % 16 != 0) return 1;
   if (!vec_ok(a.gates, a.hseq, a.aux, a.dy)) return 1;
   PersistParams p{};
@@ -2434,6 +2444,7 @@ static int launch_bwd(const SeqArgs& a, void* ws, size_t ws_bytes, cudaStream_t 
   using namespace rp;
   const int G = RNN == DS2_RNN_LSTM ? 4 : (RNN == DS2_RNN_GRU ? 3 : 1);
   const int GH = G * a.H;
+  { int mrc = materialize_w_hh(a, st); if (mrc) return mrc; }   // fp32 W_hh^T through TMA
   PersistParams p{};
   p.T = a.T; p.B = a.B; p.NB = (a.B + 7) / 8 * 8; p.H = a.H; p.D = a.D; p.NT = a.H / UT; p.G = G;
   p.training = 1;

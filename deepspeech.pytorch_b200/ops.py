@@ -226,6 +226,10 @@ class RnnLayer(torch.autograd.Function):
         check(lib.ds2_rnn_layer_fwd(C.byref(desc), ptr(x), ptr(len_dev), ptr(bn_g), ptr(bn_b), ptr(bn_rm), ptr(bn_rv),
                                     w_ih, w_hh, b_ih, b_hh, ptr(h0), ptr(c0), ptr(y), ptr(hn), ptr(cn), ptr(reserve),
                                     ptr(ws), ws.numel(), _stream()), "ds2_rnn_layer_fwd")
+        if training and _side["stream"] is not None:
+            # a tensor-core-mode training forward writes the fp16 W_hh^T of the backward sweep into `reserve` on the
+            # side stream: if the graph is dropped early, the block must not be handed out before that copy has run
+            reserve.record_stream(_side["stream"])
         ctx.desc = desc
         ctx.has_bn = bn_g is not None
         ctx.sinks = [_sink(bn_g), _sink(bn_b)] + [_sink(w) for w in weights]

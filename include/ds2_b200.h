@@ -123,7 +123,11 @@ int ds2_conv_frontend_bwd(int B, int T, const float* x, const int32_t* out_len,
  *   per direction d in [0,dirs): w_ih[d] (G*H,In)  w_hh[d] (G*H,H)  b_ih[d], b_hh[d] (G*H)
  *   bn_*: NULL for the first layer (model.py:177)
  *   h0/c0 (dirs,B,H) or NULL;  hn/cn (dirs,B,H) outputs (cn only for LSTM)
- *   reserve: ds2_rnn_reserve_floats() floats, written by fwd (training) and consumed by bwd
+ *   reserve: ds2_rnn_reserve_floats() floats, written by fwd (training) and consumed by bwd.  In the tensor-core
+ *            modes a training fwd also leaves an fp16 copy of W_hh^T there for the bwd sweep of the same step (the
+ *            weights must not change between the two calls; a bwd on a reserve that no fwd of this process filled
+ *            converts the weights itself).  With a side stream set that copy is made on it: `w_hh` stays valid
+ *            until the side stream has passed this point.
  */
 typedef struct {
   int rnn_type;      /* DS2_RNN_*                     */
