@@ -104,3 +104,28 @@ def test_conv1_wgrad_tap_columns_match_the_box_plan():
     for i in range(4):
         hits = sorted(8 * c + j - 2 * i for c in range(6) for j in range(8) if 0 <= 8 * c + j - 2 * i < 41)
         assert hits == list(range(41))
+
+
+# ---- conv2 weight gradient: taps stacked in M (conv_tc.cu: wg::KH_PER, wg::GROUPS) ----
+def test_conv2_wgrad_tap_groups_cover_every_vertical_tap_once():
+    """CTA class (parity, group) owns taps kh = parity + 2 (4 group + i), i < 4; the dz2 row of tap i for input row r is
+    d = (r + 10 - kh) / 2.  Every (d, kh) pair of the 41 x 21 products must be produced by exactly one (r, class, i)."""
+    src = (SRC / "conv_tc.cu").read_text()
+    kh_per = int(re.search(r"constexpr int KH_PER = (\d+);", src).group(1))
+    groups = int(re.search(r"constexpr int GROUPS = (\d+);", src).group(1))
+    seen = {}
+    for parity in range(2):
+        for g in range(groups):
+            kh0 = parity + 2 * kh_per * g
+            nkh = min(kh_per, (21 - 1 - kh0) // 2 + 1)
+            assert nkh >= 1
+            for r in range(parity, 81, 2):
+                for i in range(nkh):
+                    kh = kh0 + 2 * i
+                    assert (r + 10 - kh) % 2 == 0
+                    d = (r + 10 - kh0) // 2 - i
+                    if 0 <= d < 41:
+                        assert 2 * d + kh - 10 == r
+                        seen[(d, kh)] = seen.get((d, kh), 0) + 1
+    want = {(d, kh) for d in range(41) for kh in range(21) if 0 <= 2 * d + kh - 10 < 81}
+    assert set(seen) == want and all(v == 1 for v in seen.values())
