@@ -11,7 +11,7 @@ is librosa's published algorithm for `librosa.stft(y, n_fft, hop_length, win_len
 pad n_fft//2 samples on both sides (`pad_mode`: "constant" zeros since librosa 0.10, "reflect" before), frame with
 stride hop (1 + len(y)//hop frames), multiply by scipy.signal.get_window(window, n_fft, fftbins=True), rfft; then
 `librosa.magphase` -> |D|, `np.log1p`, and torch's `(x - mean) / std` with the unbiased std.  tests/test_spect.py pins
-this file against the independent `scipy.signal.stft`.
+this file against the independent `scipy.signal.stft` and `torch.stft`.
 """
 import numpy as np
 

@@ -37,6 +37,25 @@ def test_oracle_stft_matches_scipy(pad_mode, boundary):
     assert mag.shape[1] == 1 + len(y) // hop       # librosa's frame count
 
 
+@pytest.mark.parametrize("pad_mode", ["constant", "reflect"])
+def test_oracle_stft_matches_torch_stft(pad_mode):
+    """second independent pin: torch.stft(center=True) documents itself as librosa-compatible (same centring, same frame
+    count 1 + len // hop, periodic window) — the whole feature (|STFT| -> log1p -> normalise) in float64"""
+    import torch
+    y = _waves(1, 5)[0]
+    n_fft, hop = 320, 160
+    w = torch.hamming_window(n_fft, periodic=True, dtype=torch.float64)
+    Z = torch.stft(torch.from_numpy(y).double(), n_fft, hop_length=hop, win_length=n_fft, window=w, center=True,
+                   pad_mode=pad_mode, return_complex=True)
+    assert Z.shape == (161, 1 + len(y) // hop)
+    mag = SO.stft_mag(y, n_fft, hop, "hamming", pad_mode)
+    assert np.abs(mag - Z.abs().numpy()).max() <= 1e-9 * max(1.0, float(Z.abs().max()))
+    feat = torch.log1p(Z.abs())
+    feat = (feat - feat.mean()) / feat.std()
+    got = SO.compute_spectrogram(y, pad_mode=pad_mode)
+    assert np.abs(got - feat.numpy()).max() <= 1e-9
+
+
 @pytest.mark.parametrize("name", ["hamming", "hann", "blackman", "bartlett"])
 def test_window_generator_matches_scipy(name):
     assert np.abs(analysis_window(name, 320) - SO.get_window(name, 320)).max() < 1e-7
